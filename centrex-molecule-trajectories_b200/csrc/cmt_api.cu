@@ -1,0 +1,592 @@
+// cmt_api.cu -- the C ABI declared in include/cmt.h (libcmt_b200.so).
+//
+// Host side only: validation, flattening into the kernel-parameter table,
+// exact threshold/slope precomputation, launches, staging for the host-buffer
+// entry points.  No torch, no C++ types across the boundary.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <vector>
+
+#include "cmt_kernels.cuh"
+
+using namespace cmt;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t err__ = (expr);                                                         \
+        if (err__ != cudaSuccess)                                                           \
+            return fail(CMT_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), \
+                        __FILE__, __LINE__);                                                \
+    } while (0)
+
+extern "C" const char *cmt_last_error(void) { return g_err; }
+extern "C" int cmt_version(void) { return CMT_VERSION; }
+
+// ---------------------------------------------------------------------------
+// beamline handle
+// ---------------------------------------------------------------------------
+struct cmt_beamline {
+    Params P;
+    int device;
+    int max_rows;
+    int n_sm;
+    double *d_tab;      // [3][tab_total]
+    size_t tab_bytes;   // dynamic shared memory the lens/trajectory kernels need
+};
+
+// Largest double s with sqrt(s) <= R under round-to-nearest, so that the
+// reference's test `sqrt(x^2+y^2) > R` is exactly `x^2+y^2 > T`.
+static double radius_threshold(double R)
+{
+    if (std::isnan(R)) return std::numeric_limits<double>::infinity();   // rho > NaN is never true
+    if (R < 0) return -std::numeric_limits<double>::infinity();          // rho > R for every rho >= 0
+    if (std::isinf(R)) return R;
+    volatile double c = R * R;
+    const double inf = std::numeric_limits<double>::infinity();
+    for (int it = 0; it < 64 && std::sqrt((double)c) > R; ++it) c = std::nextafter((double)c, -inf);
+    for (int it = 0; it < 64; ++it) {
+        const double up = std::nextafter((double)c, inf);
+        volatile double su = std::sqrt(up);
+        if (su <= R) c = up; else break;
+    }
+    return c;
+}
+
+extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements, const cmt_table_t *tables,
+                                   int n_tables, int n_fates, int fate_detected, double g, int device,
+                                   cmt_beamline_t **out)
+{
+    if (!out) return fail(CMT_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n_elements < 0 || n_elements > CMT_MAX_ELEMENTS)
+        return fail(CMT_EINVAL, "n_elements=%d outside [0,%d]", n_elements, CMT_MAX_ELEMENTS);
+    if (n_elements > 0 && !elements) return fail(CMT_EINVAL, "elements is NULL");
+    if (n_fates < 1 || n_fates > CMT_MAX_FATES)
+        return fail(CMT_EINVAL, "n_fates=%d outside [1,%d]", n_fates, CMT_MAX_FATES);
+    if (fate_detected < 0 || fate_detected >= n_fates) return fail(CMT_EINVAL, "fate_detected out of range");
+    if (n_tables < 0 || n_tables > CMT_MAX_TABLES)
+        return fail(CMT_EINVAL, "n_tables=%d outside [0,%d]", n_tables, CMT_MAX_TABLES);
+
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(CMT_ENODEV, "no CUDA device visible");
+    }
+    if (device < 0 || device >= n_dev) return fail(CMT_EINVAL, "device %d not in [0,%d)", device, n_dev);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(CMT_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+
+    std::vector<int> tab_off(std::max(n_tables, 1), 0);
+    int tab_total = 0;
+    for (int t = 0; t < n_tables; ++t) {
+        if (!tables[t].r || !tables[t].a || tables[t].n < 2)
+            return fail(CMT_EINVAL, "lens table %d needs >= 2 points", t);
+        for (int i = 1; i < tables[t].n; ++i)
+            if (!(tables[t].r[i] > tables[t].r[i - 1]))
+                return fail(CMT_EINVAL, "lens table %d: r must be strictly ascending (index %d)", t, i);
+        tab_off[t] = tab_total;
+        tab_total += tables[t].n;
+    }
+
+    cmt_beamline *bl = new cmt_beamline();
+    memset(&bl->P, 0, sizeof(bl->P));
+    Params &P = bl->P;
+    P.n_el = n_elements;
+    P.n_fates = n_fates;
+    P.fate_detected = fate_detected;
+    P.first_lens = n_elements;
+    P.g = g;
+    P.tab_total = tab_total;
+    bl->device = device;
+    bl->n_sm = prop.multiProcessorCount;
+    bl->max_rows = 1;
+    bl->d_tab = nullptr;
+
+    for (int i = 0; i < n_elements; ++i) {
+        const cmt_element_t &s = elements[i];
+        DevElement &d = P.el[i];
+        if (i > 0 && s.z0 < elements[i - 1].z0) {
+            delete bl;
+            return fail(CMT_EINVAL, "elements must be sorted by z0 (element %d)", i);
+        }
+        if (s.fate < 0 || s.fate >= n_fates) { delete bl; return fail(CMT_EINVAL, "element %d: fate out of range", i); }
+        d.type = s.type; d.fate = s.fate; d.fate2 = s.fate2; d.n_steps = s.n_steps;
+        d.z0 = s.z0; d.z1 = s.z1;
+        switch (s.type) {
+        case CMT_CIRCULAR:
+            d.p[0] = radius_threshold(s.R);
+            bl->max_rows += 2;
+            break;
+        case CMT_RECTANGULAR:
+            d.p[0] = s.x1; d.p[1] = s.x2; d.p[2] = s.y1; d.p[3] = s.y2;
+            bl->max_rows += 2;
+            break;
+        case CMT_FIELDPLATES:
+            d.p[0] = s.x1; d.p[1] = s.x2;
+            bl->max_rows += 2;
+            break;
+        case CMT_LENS: {
+            if (s.table < 0 || s.table >= n_tables) { delete bl; return fail(CMT_EINVAL, "element %d: lens table index out of range", i); }
+            if (s.fate2 < 0 || s.fate2 >= n_fates) { delete bl; return fail(CMT_EINVAL, "element %d: fate2 out of range", i); }
+            if (s.n_steps < 0) { delete bl; return fail(CMT_EINVAL, "element %d: n_steps < 0", i); }
+            const cmt_table_t &tb = tables[s.table];
+            d.p[0] = radius_threshold(s.R);
+            d.p[1] = s.dz;
+            d.p[2] = (tb.n - 1) / (tb.r[tb.n - 1] - tb.r[0]);
+            d.tab_off = tab_off[s.table];
+            d.tab_len = tb.n;
+            bl->max_rows += 2 + s.n_steps;
+            if (P.first_lens == n_elements) P.first_lens = i;
+            break;
+        }
+        default:
+            delete bl;
+            return fail(CMT_EINVAL, "element %d: unknown type %d", i, s.type);
+        }
+    }
+
+    bl->tab_bytes = (size_t)3 * tab_total * sizeof(double);
+    if (tab_total > 0) {
+        std::vector<double> h((size_t)3 * tab_total, 0.0);
+        for (int t = 0; t < n_tables; ++t) {
+            const cmt_table_t &tb = tables[t];
+            for (int i = 0; i < tb.n; ++i) {
+                h[tab_off[t] + i] = tb.r[i];
+                h[(size_t)tab_total + tab_off[t] + i] = tb.a[i];
+                if (i + 1 < tb.n) {
+                    // np.interp: slope = (fp[j+1]-fp[j]) / (xp[j+1]-xp[j]); same IEEE ops here
+                    volatile double num = tb.a[i + 1] - tb.a[i];
+                    volatile double den = tb.r[i + 1] - tb.r[i];
+                    h[(size_t)2 * tab_total + tab_off[t] + i] = num / den;
+                }
+            }
+        }
+        if (bl->tab_bytes > 200 * 1024) { delete bl; return fail(CMT_EINVAL, "lens tables too large for shared memory (%zu B)", bl->tab_bytes); }
+        cudaError_t e = cudaSetDevice(device);
+        if (e == cudaSuccess) e = cudaMalloc(&bl->d_tab, bl->tab_bytes);
+        if (e == cudaSuccess) e = cudaMemcpy(bl->d_tab, h.data(), bl->tab_bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            if (bl->d_tab) cudaFree(bl->d_tab);
+            delete bl;
+            return fail(CMT_ECUDA, "uploading lens tables failed: %s", cudaGetErrorString(e));
+        }
+        P.tab = bl->d_tab;
+        if (bl->tab_bytes > 40 * 1024) {
+            cudaFuncSetAttribute(lens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            cudaFuncSetAttribute(trajectory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+        }
+    }
+    *out = bl;
+    return CMT_OK;
+}
+
+extern "C" void cmt_beamline_destroy(cmt_beamline_t *bl)
+{
+    if (!bl) return;
+    if (bl->d_tab) {
+        cudaSetDevice(bl->device);
+        cudaFree(bl->d_tab);
+    }
+    delete bl;
+}
+
+extern "C" int cmt_beamline_max_rows(const cmt_beamline_t *bl) { return bl ? bl->max_rows : CMT_EINVAL; }
+extern "C" int cmt_beamline_device(const cmt_beamline_t *bl) { return bl ? bl->device : CMT_EINVAL; }
+
+static constexpr size_t WS_HEADER = 256;
+
+extern "C" size_t cmt_workspace_bytes(const cmt_beamline_t *bl, int64_t n_max)
+{
+    if (!bl || n_max < 0) return 0;
+    if (bl->P.first_lens >= bl->P.n_el) return WS_HEADER;
+    return WS_HEADER + (size_t)QUEUE_COMPONENTS * sizeof(double) * (size_t)n_max;
+}
+
+// ---------------------------------------------------------------------------
+// timing (CUDA events on the launch stream)
+// ---------------------------------------------------------------------------
+struct TimedLaunch {
+    cudaEvent_t a, b;
+    int kind;
+};
+static std::mutex g_time_mu;
+static bool g_time_on = false;
+static std::vector<TimedLaunch> g_time_pending;
+static double g_time_ms[4] = {0, 0, 0, 0};
+static int64_t g_time_n[4] = {0, 0, 0, 0};
+
+struct ScopedTimer {
+    bool on;
+    cudaEvent_t a, b;
+    cudaStream_t st;
+    int kind;
+    ScopedTimer(int kind_, cudaStream_t st_) : on(false), st(st_), kind(kind_)
+    {
+        std::lock_guard<std::mutex> lk(g_time_mu);
+        on = g_time_on;
+        if (on) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~ScopedTimer()
+    {
+        if (on) {
+            cudaEventRecord(b, st);
+            std::lock_guard<std::mutex> lk(g_time_mu);
+            g_time_pending.push_back({a, b, kind});
+        }
+    }
+};
+
+extern "C" int cmt_timing_enable(int on)
+{
+    std::lock_guard<std::mutex> lk(g_time_mu);
+    g_time_on = on != 0;
+    return CMT_OK;
+}
+
+extern "C" int cmt_timing_read(double ms[4], int64_t launches[4], int reset)
+{
+    std::lock_guard<std::mutex> lk(g_time_mu);
+    for (auto &t : g_time_pending) {
+        cudaEventSynchronize(t.b);
+        float f = 0;
+        if (cudaEventElapsedTime(&f, t.a, t.b) == cudaSuccess) {
+            g_time_ms[t.kind] += f;
+            g_time_n[t.kind] += 1;
+        }
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    g_time_pending.clear();
+    for (int k = 0; k < 4; ++k) {
+        if (ms) ms[k] = g_time_ms[k];
+        if (launches) launches[k] = g_time_n[k];
+        if (reset) { g_time_ms[k] = 0; g_time_n[k] = 0; }
+    }
+    return CMT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------
+static int check_outputs(const cmt_beamline_t *bl, const cmt_outputs_t *out, int64_t n)
+{
+    if (!bl) return fail(CMT_EINVAL, "beamline handle is NULL");
+    if (!out) return fail(CMT_EINVAL, "outputs is NULL");
+    if (!out->counters) return fail(CMT_EINVAL, "outputs.counters is required");
+    if (out->final_state && out->final_ld < n) return fail(CMT_EINVAL, "outputs.final_ld < n");
+    if (out->saved_index && (!out->saved_count || out->saved_capacity < 0))
+        return fail(CMT_EINVAL, "outputs.saved_index needs saved_count and a capacity");
+    return CMT_OK;
+}
+
+static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *src, uint64_t seed,
+                     const double *ic, int64_t ic_ld, int64_t n, int64_t first_index,
+                     const cmt_outputs_t *out, void *workspace, size_t workspace_bytes, void *stream)
+{
+    int rc = check_outputs(bl, out, n);
+    if (rc) return rc;
+    if (n < 0) return fail(CMT_EINVAL, "n < 0");
+    if (n == 0) return CMT_OK;
+    const bool has_lens = bl->P.first_lens < bl->P.n_el;
+    const size_t need = cmt_workspace_bytes(bl, n);
+    if (!workspace || workspace_bytes < need)
+        return fail(CMT_ENOMEM, "workspace of %zu B given, %zu B needed for n=%lld", workspace_bytes, need,
+                    (long long)n);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return fail(CMT_EINVAL, "workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(bl->device));
+
+    Queue Q;
+    Q.count = reinterpret_cast<unsigned long long *>(workspace);
+    Q.cursor = Q.count + 1;
+    Q.q = reinterpret_cast<double *>(static_cast<char *>(workspace) + WS_HEADER);
+    Q.cap = has_lens ? n : 0;
+    CUDA_TRY(cudaMemsetAsync(workspace, 0, WS_HEADER, st));
+
+    cmt_source_t S;
+    memset(&S, 0, sizeof(S));
+    if (src) S = *src;
+
+    const int64_t tiles = (n + WALK_THREADS - 1) / WALK_THREADS;
+    const int grid_walk = (int)std::min<int64_t>(tiles, (int64_t)bl->n_sm * 8);
+    {
+        ScopedTimer tm(0, st);
+        if (philox)
+            walk_kernel<true><<<grid_walk, WALK_THREADS, 0, st>>>(bl->P, S, seed, nullptr, 0, n, first_index, *out, Q);
+        else
+            walk_kernel<false><<<grid_walk, WALK_THREADS, 0, st>>>(bl->P, S, seed, ic, ic_ld, n, first_index, *out, Q);
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (has_lens) {
+        // persistent lanes: enough CTAs to fill every SM, no more than the queue can feed
+        const int64_t max_ctas = (n + LENS_THREADS - 1) / LENS_THREADS;
+        const int grid_lens = (int)std::min<int64_t>(max_ctas, (int64_t)bl->n_sm * 4);
+        ScopedTimer tm(1, st);
+        lens_kernel<<<grid_lens, LENS_THREADS, bl->tab_bytes, st>>>(bl->P, first_index, *out, Q);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return CMT_OK;
+}
+
+extern "C" int cmt_propagate_ic(const cmt_beamline_t *bl, int64_t n, int64_t first_index, const double *ic,
+                                int64_t ic_ld, const cmt_outputs_t *out, void *workspace,
+                                size_t workspace_bytes, void *stream)
+{
+    if (n > 0 && !ic) return fail(CMT_EINVAL, "ic is NULL");
+    if (ic_ld < n) return fail(CMT_EINVAL, "ic_ld < n");
+    return propagate(bl, false, nullptr, 0, ic, ic_ld, n, first_index, out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cmt_propagate_philox(const cmt_beamline_t *bl, const cmt_source_t *src, uint64_t seed,
+                                    int64_t first_index, int64_t n, const cmt_outputs_t *out,
+                                    void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!src) return fail(CMT_EINVAL, "source is NULL");
+    if (src->pos_kind != CMT_POS_DISC && src->pos_kind != CMT_POS_GAUSS)
+        return fail(CMT_EINVAL, "unknown pos_kind %d", src->pos_kind);
+    return propagate(bl, true, src, seed, nullptr, 0, n, first_index, out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cmt_philox_draw(const cmt_source_t *src, uint64_t seed, int64_t first_index,
+                               const int64_t *index, int64_t n, double *ic, int64_t ic_ld, void *stream)
+{
+    if (!src || (n > 0 && !ic)) return fail(CMT_EINVAL, "NULL argument");
+    if (n < 0 || ic_ld < n) return fail(CMT_EINVAL, "bad n / ic_ld");
+    if (src->pos_kind != CMT_POS_DISC && src->pos_kind != CMT_POS_GAUSS)
+        return fail(CMT_EINVAL, "unknown pos_kind %d", src->pos_kind);
+    if (n == 0) return CMT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    {
+        ScopedTimer tm(3, st);
+        draw_kernel<<<grid, 256, 0, st>>>(*src, seed, first_index, index, n, ic, ic_ld);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return CMT_OK;
+}
+
+extern "C" int cmt_trajectories(const cmt_beamline_t *bl, int64_t n, const double *state, int n_comp,
+                                int64_t state_ld, const int64_t *select, int64_t select_base, double *rows,
+                                int32_t max_rows, int32_t *n_rows, uint8_t *fate, void *stream)
+{
+    if (!bl) return fail(CMT_EINVAL, "beamline handle is NULL");
+    if (n < 0) return fail(CMT_EINVAL, "n < 0");
+    if (n == 0) return CMT_OK;
+    if (!state || !rows) return fail(CMT_EINVAL, "state/rows is NULL");
+    if (n_comp != 6 && n_comp != 10) return fail(CMT_EINVAL, "n_comp must be 6 or 10");
+    if (max_rows < 1) return fail(CMT_EINVAL, "max_rows < 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(bl->device));
+    const int grid = (int)((n + TRAJ_THREADS - 1) / TRAJ_THREADS);
+    {
+        ScopedTimer tm(2, st);
+        trajectory_kernel<<<grid, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, n, state, n_comp, state_ld, select,
+                                                                      select_base, rows, max_rows, n_rows, fate);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return CMT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer entry points: chunked, two streams, copies straight from/to the
+// caller's buffers (truly asynchronous when those are pinned, still correct
+// when they are pageable).  H2D of chunk k+1 overlaps the kernels of chunk k.
+// ---------------------------------------------------------------------------
+namespace {
+
+struct HostPipe {
+    int device = -1;
+    int64_t chunk = 0;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    double *d_ic[2] = {nullptr, nullptr};
+    uint8_t *d_fate[2] = {nullptr, nullptr};
+    double *d_final[2] = {nullptr, nullptr};
+    void *d_ws[2] = {nullptr, nullptr};
+    size_t ws_bytes = 0;
+    int64_t *d_cnt = nullptr;   // [CMT_MAX_FATES + 4]
+
+    void release()
+    {
+        if (device < 0) return;
+        cudaSetDevice(device);
+        for (int k = 0; k < 2; ++k) {
+            if (st[k]) cudaStreamDestroy(st[k]);
+            cudaFree(d_ic[k]); cudaFree(d_fate[k]); cudaFree(d_final[k]); cudaFree(d_ws[k]);
+            st[k] = nullptr; d_ic[k] = nullptr; d_fate[k] = nullptr; d_final[k] = nullptr; d_ws[k] = nullptr;
+        }
+        cudaFree(d_cnt);
+        d_cnt = nullptr;
+        device = -1;
+    }
+    ~HostPipe() { release(); }
+};
+
+std::mutex g_pipe_mu;
+HostPipe g_pipe;
+
+int pipe_prepare(HostPipe &p, const cmt_beamline_t *bl, int64_t chunk, bool want_ic, bool want_fate, bool want_final)
+{
+    const size_t ws = cmt_workspace_bytes(bl, chunk);
+    const bool ok = p.device == bl->device && p.chunk >= chunk && p.ws_bytes >= cmt_workspace_bytes(bl, p.chunk) &&
+                    (!want_final || p.d_final[0]) && (!want_ic || p.d_ic[0]) && (!want_fate || p.d_fate[0]);
+    if (ok) return CMT_OK;
+    const bool keep_ic = want_ic || p.d_ic[0], keep_fate = want_fate || p.d_fate[0], keep_final = want_final || p.d_final[0];
+    chunk = std::max(chunk, p.device == bl->device ? p.chunk : (int64_t)0);
+    p.release();
+    CUDA_TRY(cudaSetDevice(bl->device));
+    p.device = bl->device;
+    p.chunk = chunk;
+    p.ws_bytes = std::max(ws, cmt_workspace_bytes(bl, chunk));
+    for (int k = 0; k < 2; ++k) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&p.st[k], cudaStreamNonBlocking));
+        CUDA_TRY(cudaMalloc(&p.d_ws[k], p.ws_bytes));
+        if (keep_ic) CUDA_TRY(cudaMalloc(&p.d_ic[k], (size_t)6 * chunk * sizeof(double)));
+        if (keep_fate) CUDA_TRY(cudaMalloc(&p.d_fate[k], (size_t)chunk));
+        if (keep_final) CUDA_TRY(cudaMalloc(&p.d_final[k], (size_t)10 * chunk * sizeof(double)));
+    }
+    CUDA_TRY(cudaMalloc(&p.d_cnt, (CMT_MAX_FATES + 4) * sizeof(int64_t)));
+    return CMT_OK;
+}
+
+int pipe_collect(HostPipe &p, const cmt_beamline_t *bl, int64_t *counters_host, int64_t *work_host)
+{
+    for (int k = 0; k < 2; ++k) CUDA_TRY(cudaStreamSynchronize(p.st[k]));
+    int64_t h[CMT_MAX_FATES + 4];
+    CUDA_TRY(cudaMemcpy(h, p.d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int f = 0; f < bl->P.n_fates; ++f) counters_host[f] += h[f];
+    if (work_host) for (int k = 0; k < 4; ++k) work_host[k] += h[CMT_MAX_FATES + k];
+    return CMT_OK;
+}
+
+}  // namespace
+
+extern "C" int cmt_run_host_ic(const cmt_beamline_t *bl, int64_t n, const double *ic_host, uint8_t *fate_host,
+                               double *final_host, int64_t *counters_host, int64_t *work_host)
+{
+    if (!bl) return fail(CMT_EINVAL, "beamline handle is NULL");
+    if (n < 0) return fail(CMT_EINVAL, "n < 0");
+    if (!counters_host) return fail(CMT_EINVAL, "counters_host is NULL");
+    if (n == 0) return CMT_OK;
+    if (!ic_host) return fail(CMT_EINVAL, "ic_host is NULL");
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    HostPipe &p = g_pipe;
+    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 21);
+    int rc = pipe_prepare(p, bl, chunk, true, fate_host != nullptr, final_host != nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(p.d_cnt, 0, (CMT_MAX_FATES + 4) * sizeof(int64_t), p.st[0]));
+    CUDA_TRY(cudaStreamSynchronize(p.st[0]));
+
+    const size_t dpitch = (size_t)p.chunk * sizeof(double), hpitch = (size_t)n * sizeof(double);
+    const int64_t n_chunks = (n + chunk - 1) / chunk;
+    for (int64_t ci = 0; ci < n_chunks; ++ci) {
+        const int k = (int)(ci & 1);
+        const int64_t off = ci * chunk, len = std::min<int64_t>(chunk, n - off);
+        CUDA_TRY(cudaMemcpy2DAsync(p.d_ic[k], dpitch, ic_host + off, hpitch, (size_t)len * sizeof(double), 6,
+                                   cudaMemcpyHostToDevice, p.st[k]));
+        cmt_outputs_t O;
+        memset(&O, 0, sizeof(O));
+        O.fate = fate_host ? p.d_fate[k] : nullptr;
+        O.final_state = final_host ? p.d_final[k] : nullptr;
+        O.final_ld = p.chunk;
+        O.counters = p.d_cnt;
+        O.work = p.d_cnt + CMT_MAX_FATES;
+        rc = cmt_propagate_ic(bl, len, off, p.d_ic[k], p.chunk, &O, p.d_ws[k], p.ws_bytes, p.st[k]);
+        if (rc) return rc;
+        if (fate_host)
+            CUDA_TRY(cudaMemcpyAsync(fate_host + off, p.d_fate[k], (size_t)len, cudaMemcpyDeviceToHost, p.st[k]));
+        if (final_host)
+            CUDA_TRY(cudaMemcpy2DAsync(final_host + off, hpitch, p.d_final[k], dpitch, (size_t)len * sizeof(double),
+                                       10, cudaMemcpyDeviceToHost, p.st[k]));
+    }
+    return pipe_collect(p, bl, counters_host, work_host);
+}
+
+extern "C" int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t *src, uint64_t seed,
+                                   int64_t first_index, int64_t n, int64_t *counters_host, int64_t *work_host)
+{
+    if (!bl) return fail(CMT_EINVAL, "beamline handle is NULL");
+    if (n < 0) return fail(CMT_EINVAL, "n < 0");
+    if (!counters_host || !src) return fail(CMT_EINVAL, "NULL argument");
+    if (n == 0) return CMT_OK;
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    HostPipe &p = g_pipe;
+    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 24);
+    int rc = pipe_prepare(p, bl, chunk, false, false, false);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(p.d_cnt, 0, (CMT_MAX_FATES + 4) * sizeof(int64_t), p.st[0]));
+    CUDA_TRY(cudaStreamSynchronize(p.st[0]));
+    const int64_t n_chunks = (n + chunk - 1) / chunk;
+    for (int64_t ci = 0; ci < n_chunks; ++ci) {
+        const int k = (int)(ci & 1);
+        const int64_t off = ci * chunk, len = std::min<int64_t>(chunk, n - off);
+        cmt_outputs_t O;
+        memset(&O, 0, sizeof(O));
+        O.counters = p.d_cnt;
+        O.work = p.d_cnt + CMT_MAX_FATES;
+        rc = cmt_propagate_philox(bl, src, seed, first_index + off, len, &O, p.d_ws[k], p.ws_bytes, p.st[k]);
+        if (rc) return rc;
+    }
+    return pipe_collect(p, bl, counters_host, work_host);
+}
+
+// ---------------------------------------------------------------------------
+// FP64 pipe ceilings
+// ---------------------------------------------------------------------------
+extern "C" int cmt_fp64_peak(int device, double *dfma_per_s, double *dadd_per_s)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    double *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, sizeof(double)));
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    const int grid = prop.multiProcessorCount * 8, iters = 1 << 15;
+    double best[2] = {0, 0};
+    for (int which = 0; which < 2; ++which) {
+        for (int rep = 0; rep < 4; ++rep) {
+            CUDA_TRY(cudaEventRecord(a));
+            if (which == 0) fp64_peak_kernel<true><<<grid, 256>>>(d_out, iters, 1.0);
+            else fp64_peak_kernel<false><<<grid, 256>>>(d_out, iters, 1.0);
+            CUDA_TRY(cudaEventRecord(b));
+            CUDA_TRY(cudaEventSynchronize(b));
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+            const double ops = (double)grid * 256.0 * iters * 8.0;
+            if (rep > 0) best[which] = std::max(best[which], ops / (ms * 1e-3));
+        }
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d_out);
+    if (dfma_per_s) *dfma_per_s = best[0];
+    if (dadd_per_s) *dadd_per_s = best[1];
+    return CMT_OK;
+}

@@ -1,0 +1,359 @@
+// cmt_kernels.cuh -- the kernels of the propagation path (sm_100a).
+//
+//   walk_kernel   one molecule per thread: source (HBM SoA load or Philox),
+//                 every element up to and including the first lens' entrance
+//                 plane; dead molecules retire here (fate byte, histogram,
+//                 optional final row, optional saved-index append); survivors
+//                 are compacted (warp ballot + one atomic per warp) into the
+//                 lens queue.
+//   lens_kernel   persistent lanes pull survivors from the queue and run a
+//                 per-lane state machine: RK steps while inside a lens, whole
+//                 apertures otherwise, until the molecule dies or is detected;
+//                 an idle lane immediately pulls the next survivor, so warps
+//                 stay full while molecules die at different steps.
+//   trajectory_kernel  re-propagates selected molecules and writes every row.
+//   draw_kernel   materialises the source's samples.
+//
+// HBM layout: initial conditions and final rows are SoA FP64 ([component][n]),
+// so a warp's 32 loads/stores per component are one contiguous 256 B segment;
+// fates are one byte per molecule.
+#pragma once
+
+#include "cmt_device.cuh"
+
+namespace cmt {
+
+constexpr int WALK_THREADS = 256;
+constexpr int LENS_THREADS = 128;
+constexpr int TRAJ_THREADS = 64;
+constexpr int QUEUE_COMPONENTS = 8;  // x,y,z,vx,vy,vz,t + global index bits
+
+struct Queue {
+    unsigned long long *count;   // survivors appended by walk_kernel
+    unsigned long long *cursor;  // next survivor to hand out in lens_kernel
+    double *q;                   // [QUEUE_COMPONENTS][cap]
+    int64_t cap;
+};
+
+struct BlockAcc {
+    unsigned int hist[CMT_MAX_FATES];
+    unsigned long long work[4];
+};
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// Append `v` for every lane with pred set: one atomic per warp.
+__device__ __forceinline__ long long warp_append(bool pred, unsigned long long *cursor)
+{
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return -1;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(cursor, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return pred ? (long long)(base + __popc(mask & ((1u << lane_id()) - 1u))) : -1;
+}
+
+__device__ __forceinline__ void block_acc_init(BlockAcc &acc)
+{
+    for (int i = threadIdx.x; i < CMT_MAX_FATES; i += blockDim.x) acc.hist[i] = 0;
+    if (threadIdx.x < 4) acc.work[threadIdx.x] = 0;
+    __syncthreads();
+}
+
+__device__ __forceinline__ void block_acc_flush(BlockAcc &acc, const Params &P, const cmt_outputs_t &O)
+{
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.n_fates; i += blockDim.x)
+        if (acc.hist[i]) atomicAdd((unsigned long long *)O.counters + i, (unsigned long long)acc.hist[i]);
+    if (O.work && threadIdx.x < 4 && acc.work[threadIdx.x])
+        atomicAdd((unsigned long long *)O.work + threadIdx.x, acc.work[threadIdx.x]);
+}
+
+__device__ __forceinline__ void warp_add_work(BlockAcc &acc, int which, unsigned v)
+{
+    v = __reduce_add_sync(0xffffffffu, v);
+    if (lane_id() == 0 && v) atomicAdd(&acc.work[which], (unsigned long long)v);
+}
+
+// Retire a molecule: fate byte, histogram, optional final row, optional saved index.
+// Must be called by all 32 lanes of a warp (`done` selects the retiring ones).
+__device__ __forceinline__ void retire(bool done, int fate, const Mol &m, int64_t local, int64_t global_index,
+                                       BlockAcc &acc, const cmt_outputs_t &O)
+{
+    const unsigned done_mask = __ballot_sync(0xffffffffu, done);
+    if (done_mask == 0) return;
+    if (done) {
+        // one shared-memory atomic per distinct fate in the warp, not per lane
+        const unsigned peers = __match_any_sync(done_mask, fate);
+        if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&acc.hist[fate], (unsigned)__popc(peers));
+        if (O.fate) O.fate[local] = (uint8_t)fate;
+        if (O.final_state) {
+            double *f = O.final_state + local;
+            const int64_t ld = O.final_ld;
+            f[0 * ld] = m.x;  f[1 * ld] = m.y;  f[2 * ld] = m.z;
+            f[3 * ld] = m.vx; f[4 * ld] = m.vy; f[5 * ld] = m.vz;
+            f[6 * ld] = m.ax; f[7 * ld] = m.ay; f[8 * ld] = 0.0;
+            f[9 * ld] = m.t;
+        }
+    }
+    if (O.saved_index) {
+        const bool save = done && ((O.save_mask >> fate) & 1ull);
+        const long long pos = warp_append(save, (unsigned long long *)O.saved_count);
+        if (save && pos < O.saved_capacity) O.saved_index[pos] = global_index;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// walk kernel
+// ---------------------------------------------------------------------------
+template <bool PHILOX>
+__global__ void __launch_bounds__(WALK_THREADS)
+walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source_t S, uint64_t seed,
+            const double *__restrict__ ic, int64_t ic_ld, int64_t n, int64_t first_index,
+            const __grid_constant__ cmt_outputs_t O, Queue Q)
+{
+    __shared__ BlockAcc acc;
+    block_acc_init(acc);
+
+    const int n_walk = P.first_lens < P.n_el ? P.first_lens + 1 : P.n_el;
+    const int64_t n_tiles = (n + WALK_THREADS - 1) / WALK_THREADS;
+    unsigned rows_total = 0, entries = 0;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i = tile * WALK_THREADS + threadIdx.x;
+        const bool valid = i < n;
+        Mol m;
+        if (valid) {
+            if (PHILOX) {
+                draw(S, seed, (uint64_t)(first_index + i), m);
+            } else {
+                m.x = ic[0 * ic_ld + i]; m.y = ic[1 * ic_ld + i]; m.z = ic[2 * ic_ld + i];
+                m.vx = ic[3 * ic_ld + i]; m.vy = ic[4 * ic_ld + i]; m.vz = ic[5 * ic_ld + i];
+            }
+            // a literal -0.0 becomes +0.0, as the reference's first "+ a*dt" does
+            m.x = add(m.x, 0.0); m.z = add(m.z, 0.0); m.vx = add(m.vx, 0.0); m.vz = add(m.vz, 0.0);
+        } else {
+            m.x = m.y = m.z = m.vx = m.vy = 0.0; m.vz = 1.0;
+        }
+        m.t = 0.0; m.ax = 0.0; m.ay = -P.g;
+
+        CountRows rec;
+        int fate = -1;
+        bool to_lens = false;
+        if (valid) {
+            for (int e = 0; e < n_walk; ++e) {
+                const DevElement &E = P.el[e];
+                if (E.type == CMT_LENS) {
+                    to_plane(m, E.z0, P.g, rec);
+                    if (outside_radius(m, E.p[0])) fate = E.fate;   // "Lens entrance"
+                    else to_lens = true;
+                    break;
+                }
+                fate = do_aperture(E, m, P.g, rec);
+                if (fate >= 0) break;
+            }
+            if (fate < 0 && !to_lens) fate = P.fate_detected;
+        }
+        rows_total += rec.n;
+        entries += to_lens ? 1u : 0u;
+
+        // survivors -> lens queue (compacted)
+        const long long qpos = warp_append(to_lens, Q.count);
+        if (to_lens && qpos < Q.cap) {
+            double *q = Q.q + qpos;
+            q[0 * Q.cap] = m.x;  q[1 * Q.cap] = m.y;  q[2 * Q.cap] = m.z;
+            q[3 * Q.cap] = m.vx; q[4 * Q.cap] = m.vy; q[5 * Q.cap] = m.vz;
+            q[6 * Q.cap] = m.t;
+            q[7 * Q.cap] = __longlong_as_double(i);
+        }
+        retire(valid && !to_lens, fate, m, i, first_index + i, acc, O);
+    }
+    warp_add_work(acc, 0, rows_total);
+    warp_add_work(acc, 3, entries);
+    block_acc_flush(acc, P, O);
+}
+
+// ---------------------------------------------------------------------------
+// lens kernel: persistent lanes, per-lane state machine
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(LENS_THREADS)
+lens_kernel(const __grid_constant__ Params P, int64_t first_index,
+            const __grid_constant__ cmt_outputs_t O, Queue Q)
+{
+    extern __shared__ double smem_tab[];
+    __shared__ BlockAcc acc;
+    for (int i = threadIdx.x; i < 3 * P.tab_total; i += blockDim.x) smem_tab[i] = P.tab[i];
+    block_acc_init(acc);
+
+    const unsigned long long count = min(*Q.count, (unsigned long long)Q.cap);
+    unsigned rows_total = 0, steps_total = 0, oob_total = 0;
+
+    Mol m;
+    m.x = m.y = m.z = m.vx = m.vy = m.t = m.ax = m.ay = 0.0; m.vz = 1.0;
+    int64_t local = 0;
+    int e = 0;          // element being processed
+    int step = -1;      // >= 0: RK steps already taken inside lens e
+    bool have = false;
+    bool drained = false;   // warp-uniform: the queue has nothing left
+    Table tb;
+    tb.r = tb.a = tb.s = smem_tab; tb.n = 2; tb.inv_h = 0.0;
+    LensConsts lc;
+    lc.dt = 0.0; lc.zinc = 0.0;
+
+    for (;;) {
+        // ---- refill idle lanes ----
+        const unsigned idle = __ballot_sync(0xffffffffu, !have);
+        if (idle) {
+            if (!drained) {
+                const int leader = __ffs(idle) - 1;
+                unsigned long long base = 0;
+                if ((int)lane_id() == leader) base = atomicAdd(Q.cursor, (unsigned long long)__popc(idle));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!have) {
+                    const unsigned long long k = base + __popc(idle & ((1u << lane_id()) - 1u));
+                    if (k < count) {
+                        const double *q = Q.q + k;
+                        m.x = q[0 * Q.cap];  m.y = q[1 * Q.cap];  m.z = q[2 * Q.cap];
+                        m.vx = q[3 * Q.cap]; m.vy = q[4 * Q.cap]; m.vz = q[5 * Q.cap];
+                        m.t = q[6 * Q.cap];
+                        local = __double_as_longlong(q[7 * Q.cap]);
+                        m.ax = 0.0; m.ay = -P.g;
+                        e = P.first_lens;
+                        step = 0;
+                        tb = table_of(P, P.el[e], smem_tab);
+                        lc = lens_consts(P.el[e], m);
+                        have = true;
+                    }
+                }
+                if (base + __popc(idle) >= count) drained = true;
+            }
+            if (__ballot_sync(0xffffffffu, have) == 0) break;
+        }
+
+        // ---- advance every busy lane by one RK step or one aperture ----
+        int fate = -1;
+        if (have) {
+            CountRows rec;
+            if (step >= 0) {
+                const DevElement &E = P.el[e];
+                int oob = 0;
+                lens_step(tb, lc, m, P.g, oob);
+                oob_total += oob;
+                ++steps_total;
+                ++rows_total;
+                ++step;
+                if (outside_radius(m, E.p[0])) fate = E.fate2;          // "Inside lens"
+                else if (step >= E.n_steps) {
+                    lens_exit(E, m, P.g, rec);
+                    step = -1;
+                    ++e;
+                }
+            } else if (e >= P.n_el) {
+                fate = P.fate_detected;
+            } else {
+                const DevElement &E = P.el[e];
+                if (E.type == CMT_LENS) {
+                    to_plane(m, E.z0, P.g, rec);
+                    if (outside_radius(m, E.p[0])) fate = E.fate;       // "Lens entrance"
+                    else {
+                        step = 0;
+                        tb = table_of(P, E, smem_tab);
+                        lc = lens_consts(E, m);
+                        if (E.n_steps <= 0) { lens_exit(E, m, P.g, rec); step = -1; ++e; }
+                    }
+                } else {
+                    fate = do_aperture(E, m, P.g, rec);
+                    ++e;
+                }
+            }
+            rows_total += rec.n;
+        }
+        const bool done = have && fate >= 0;
+        retire(done, fate, m, local, first_index + local, acc, O);
+        if (done) have = false;
+    }
+    warp_add_work(acc, 0, rows_total);
+    warp_add_work(acc, 1, steps_total);
+    warp_add_work(acc, 2, oob_total);
+    block_acc_flush(acc, P, O);
+}
+
+// ---------------------------------------------------------------------------
+// trajectory kernel: every row of selected molecules
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TRAJ_THREADS)
+trajectory_kernel(const __grid_constant__ Params P, int64_t n, const double *__restrict__ state, int n_comp,
+                  int64_t state_ld, const int64_t *__restrict__ select, int64_t select_base,
+                  double *__restrict__ rows, int max_rows, int32_t *__restrict__ n_rows,
+                  uint8_t *__restrict__ fate_out)
+{
+    extern __shared__ double smem_tab[];
+    for (int i = threadIdx.x; i < 3 * P.tab_total; i += blockDim.x) smem_tab[i] = P.tab[i];
+    __syncthreads();
+
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int64_t col = select ? select[j] - select_base : j;
+    Mol m;
+    m.x = state[0 * state_ld + col]; m.y = state[1 * state_ld + col]; m.z = state[2 * state_ld + col];
+    m.vx = state[3 * state_ld + col]; m.vy = state[4 * state_ld + col]; m.vz = state[5 * state_ld + col];
+    if (n_comp >= 10) {
+        // resume from an arbitrary row (BeamlineElement.propagate_through on a live Molecule)
+        m.ax = state[6 * state_ld + col]; m.ay = state[7 * state_ld + col];
+        m.t = state[9 * state_ld + col];
+    } else {
+        m.ax = 0.0; m.ay = -P.g; m.t = 0.0;
+    }
+    WriteRows rec;
+    rec.base = rows + (size_t)j * max_rows * CMT_ROW_DOUBLES;
+    rec.max_rows = max_rows;
+    rec.row(m);  // Molecule.init_trajectory stores the initial row, molecule.py:24
+
+    int fate = -1, steps = 0, oob = 0;
+    for (int e = 0; e < P.n_el && fate < 0; ++e) {
+        const DevElement &E = P.el[e];
+        if (E.type == CMT_LENS) fate = do_lens(P, E, smem_tab, m, rec, steps, oob);
+        else fate = do_aperture(E, m, P.g, rec);
+    }
+    if (fate < 0) fate = P.fate_detected;
+    if (n_rows) n_rows[j] = rec.n;
+    if (fate_out) fate_out[j] = (uint8_t)fate;
+}
+
+// ---------------------------------------------------------------------------
+// source only
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+draw_kernel(const __grid_constant__ cmt_source_t S, uint64_t seed, int64_t first_index,
+            const int64_t *__restrict__ index, int64_t n, double *__restrict__ ic, int64_t ld)
+{
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        Mol m;
+        draw(S, seed, (uint64_t)(index ? index[j] : first_index + j), m);
+        ic[0 * ld + j] = m.x; ic[1 * ld + j] = m.y; ic[2 * ld + j] = m.z;
+        ic[3 * ld + j] = m.vx; ic[4 * ld + j] = m.vy; ic[5 * ld + j] = m.vz;
+    }
+}
+
+// FP64 pipe ceiling probes: 8 independent chains per thread, no memory traffic.
+template <bool FMA>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        if (FMA) {
+            a0 = __fma_rn(a0, b, c); a1 = __fma_rn(a1, b, c); a2 = __fma_rn(a2, b, c); a3 = __fma_rn(a3, b, c);
+            a4 = __fma_rn(a4, b, c); a5 = __fma_rn(a5, b, c); a6 = __fma_rn(a6, b, c); a7 = __fma_rn(a7, b, c);
+        } else {
+            a0 = __dadd_rn(a0, c); a1 = __dadd_rn(a1, c); a2 = __dadd_rn(a2, c); a3 = __dadd_rn(a3, c);
+            a4 = __dadd_rn(a4, c); a5 = __dadd_rn(a5, c); a6 = __dadd_rn(a6, c); a7 = __dadd_rn(a7, c);
+        }
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.6789) out[0] = s;  // keep the chains alive
+}
+
+}  // namespace cmt

@@ -1,0 +1,365 @@
+"""Host-side orchestration of the CUDA propagation path.
+
+PyTorch is plumbing only: device memory (tensors), the current CUDA stream and
+`torch.distributed` for the tiny Counter all-reduce.  All arithmetic on the
+path happens in libcmt_b200.so (csrc/), reached through the C ABI in
+include/cmt.h.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as nat
+
+G = 9.80665  # scipy.constants.g (molecule.py:6)
+DEFAULT_CHUNK = 1 << 24          # molecules per launch
+ROW_BUDGET_BYTES = 1 << 30       # device bytes per saved-trajectory batch
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+# ---------------------------------------------------------------------------
+# flattening: Beamline -> element table + lens tables + fate names
+# ---------------------------------------------------------------------------
+@dataclass
+class FlatBeamline:
+    elements: List[nat.Element]
+    tables: List[Tuple[np.ndarray, np.ndarray]]
+    fate_names: List[str]
+    max_rows: int
+    key: bytes = b""
+
+    @property
+    def fate_detected(self) -> int:
+        return self.fate_names.index("Detected")
+
+    def fate_id(self, name: str) -> Optional[int]:
+        return self.fate_names.index(name) if name in self.fate_names else None
+
+    def save_mask(self, names: Sequence[str]) -> int:
+        mask = 0
+        for nm in names:
+            k = self.fate_id(nm)
+            if k is not None:
+                mask |= 1 << k
+        return mask
+
+
+def flatten(elements: Sequence) -> FlatBeamline:
+    """Flatten beamline elements (already sorted by z0, beamline.py:40-45).
+
+    Fate strings follow the reference: an aperture's `name`
+    (apertures.py:113,188,242,264), the literals "Lens entrance"/"Inside lens"
+    for a lens (electrostatic_lens.py:63,117) and "Detected" (beamline.py:34-35).
+    """
+    from .beamline_elements.apertures import CircularAperture, FieldPlates, RectangularAperture
+    from .beamline_elements.electrostatic_lens import ElectrostaticLens
+
+    if len(elements) > nat.CMT_MAX_ELEMENTS:
+        raise ValueError(f"at most {nat.CMT_MAX_ELEMENTS} beamline elements are supported")
+    names: List[str] = []
+
+    def fid(name: str) -> int:
+        if name not in names:
+            names.append(name)
+        return names.index(name)
+
+    out: List[nat.Element] = []
+    tables: List[Tuple[np.ndarray, np.ndarray]] = []
+    max_rows = 1
+    for e in elements:
+        t = nat.Element()
+        t.z0, t.z1 = float(e.z0), float(e.z1)
+        if isinstance(e, CircularAperture):
+            t.type, t.fate, t.R = nat.CIRCULAR, fid(e.name), float(e.d) / 2
+            max_rows += 2
+        elif isinstance(e, RectangularAperture):
+            t.type, t.fate = nat.RECTANGULAR, fid(e.name)
+            t.x1, t.x2, t.y1, t.y2 = float(e.x1), float(e.x2), float(e.y1), float(e.y2)
+            max_rows += 2
+        elif isinstance(e, FieldPlates):
+            t.type, t.fate = nat.FIELDPLATES, fid(e.name)
+            t.x1, t.x2 = float(e.x1), float(e.x2)
+            max_rows += 2
+        elif isinstance(e, ElectrostaticLens):
+            t.type = nat.LENS
+            t.fate, t.fate2 = fid("Lens entrance"), fid("Inside lens")
+            t.R, t.dz = float(e.d) / 2, float(e.dz)
+            t.n_steps = int(np.rint(e.L / e.dz))
+            r, a = e.acceleration_table()
+            t.table = len(tables)
+            tables.append((np.ascontiguousarray(r, dtype=np.float64), np.ascontiguousarray(a, dtype=np.float64)))
+            max_rows += 2 + t.n_steps
+        else:
+            raise TypeError(
+                f"beamline element {type(e).__name__!r} has no CUDA implementation "
+                "(supported: CircularAperture, RectangularAperture, FieldPlates, ElectrostaticLens)"
+            )
+        out.append(t)
+    fid("Detected")
+    if len(names) > nat.CMT_MAX_FATES:
+        raise ValueError(f"at most {nat.CMT_MAX_FATES} distinct fates are supported")
+    if len(tables) > nat.CMT_MAX_TABLES:
+        raise ValueError(f"at most {nat.CMT_MAX_TABLES} lenses are supported")
+    key = b"".join(bytes(t) for t in out) + b"|".join(r.tobytes() + a.tobytes() for r, a in tables)
+    key += "|".join(names).encode()
+    return FlatBeamline(out, tables, names, max_rows, key)
+
+
+# ---------------------------------------------------------------------------
+# device handle
+# ---------------------------------------------------------------------------
+class DeviceBeamline:
+    """Owns a cmt_beamline_t on one GPU."""
+
+    def __init__(self, flat: FlatBeamline, device: int):
+        lib = nat.lib()
+        self.flat = flat
+        self.device = int(device)
+        arr = (nat.Element * max(len(flat.elements), 1))(*flat.elements)
+        tabs = (nat.Table * max(len(flat.tables), 1))()
+        for k, (r, a) in enumerate(flat.tables):
+            tabs[k].r = r.ctypes.data_as(C.POINTER(C.c_double))
+            tabs[k].a = a.ctypes.data_as(C.POINTER(C.c_double))
+            tabs[k].n = len(r)
+        handle = C.c_void_p()
+        nat.check(lib.cmt_beamline_create(arr, len(flat.elements), tabs, len(flat.tables), len(flat.fate_names),
+                                          flat.fate_detected, G, self.device, C.byref(handle)))
+        self.handle = handle
+        self.max_rows = lib.cmt_beamline_max_rows(handle)
+
+    def workspace_bytes(self, n: int) -> int:
+        return int(nat.lib().cmt_workspace_bytes(self.handle, int(n)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                nat.lib().cmt_beamline_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+_handles: Dict[Tuple[bytes, int], DeviceBeamline] = {}
+
+
+def device_beamline(flat: FlatBeamline, device: int) -> DeviceBeamline:
+    k = (flat.key, int(device))
+    h = _handles.get(k)
+    if h is None:
+        if len(_handles) > 64:
+            _handles.clear()
+        h = _handles[k] = DeviceBeamline(flat, device)
+    return h
+
+
+def resolve_device(device=None) -> int:
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise nat.NativeError("no CUDA device is available and there is no CPU fallback for the propagation path")
+    if device is None:
+        return torch.cuda.current_device()
+    if isinstance(device, int):
+        return device
+    d = torch.device(device)
+    return d.index if d.index is not None else torch.cuda.current_device()
+
+
+def _stream_ptr(device: int) -> int:
+    return int(_torch().cuda.current_stream(device).cuda_stream)
+
+
+# ---------------------------------------------------------------------------
+# source description
+# ---------------------------------------------------------------------------
+def make_source(vdist, xdist) -> Optional[nat.Source]:
+    """Distribution objects -> device source record, or None when the pair has
+    no on-device generator (then draw() is called on the host and replayed)."""
+    from .distributions import (CeNTREXPositionDistribution, CeNTREXVelocityDistribution,
+                                GaussianPositionDistribution)
+
+    if type(vdist) is not CeNTREXVelocityDistribution:
+        return None
+    s = nat.Source()
+    s.vmean[:] = [vdist.vx, vdist.vy, vdist.vz]
+    s.vsigma[:] = [vdist.sigmax, vdist.sigmay, vdist.sigmaz]
+    if type(xdist) is CeNTREXPositionDistribution:
+        s.pos_kind, s.p0, s.p1 = nat.POS_DISC, xdist.d / 2, 0.0
+    elif type(xdist) is GaussianPositionDistribution:
+        s.pos_kind, s.p0, s.p1 = nat.POS_GAUSS, xdist.sigmax, xdist.sigmay
+    else:
+        return None
+    s.z = xdist.z
+    return s
+
+
+# ---------------------------------------------------------------------------
+# one propagation call over device-resident data
+# ---------------------------------------------------------------------------
+@dataclass
+class PropagateResult:
+    counters: "object"                     # torch int64 [n_fates] (device)
+    work: "object"                         # torch int64 [4] (device)
+    fate: Optional["object"] = None        # torch uint8 [n]
+    final: Optional["object"] = None       # torch float64 [10, n]
+    saved_index: Optional["object"] = None  # torch int64 [n_saved], sorted
+    fate_names: List[str] = field(default_factory=list)
+
+
+class Propagator:
+    """Reusable launch context: beamline handle + scratch buffers on one device."""
+
+    def __init__(self, elements_or_flat, device=None):
+        self.flat = elements_or_flat if isinstance(elements_or_flat, FlatBeamline) else flatten(elements_or_flat)
+        self.device = resolve_device(device)
+        self.dev = device_beamline(self.flat, self.device)
+        self._ws = None
+        torch = _torch()
+        self.tdev = torch.device("cuda", self.device)
+        self.counters = torch.zeros(len(self.flat.fate_names), dtype=torch.int64, device=self.tdev)
+        self.work = torch.zeros(4, dtype=torch.int64, device=self.tdev)
+        self.saved_count = torch.zeros(1, dtype=torch.int64, device=self.tdev)
+
+    def reset(self):
+        self.counters.zero_()
+        self.work.zero_()
+
+    def _workspace(self, n: int):
+        torch = _torch()
+        need = self.dev.workspace_bytes(n)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.tdev)
+        return self._ws
+
+    def _outputs(self, n, want_fate, want_final, save_mask, saved_buf):
+        torch = _torch()
+        O = nat.Outputs()
+        fate = final = None
+        if want_fate:
+            fate = torch.empty(n, dtype=torch.uint8, device=self.tdev)
+            O.fate = fate.data_ptr()
+        if want_final:
+            final = torch.empty((10, n), dtype=torch.float64, device=self.tdev)
+            O.final_state, O.final_ld = final.data_ptr(), n
+        O.counters = self.counters.data_ptr()
+        O.work = self.work.data_ptr()
+        if save_mask:
+            self.saved_count.zero_()
+            O.saved_index = saved_buf.data_ptr()
+            O.saved_count = self.saved_count.data_ptr()
+            O.saved_capacity = saved_buf.numel()
+            O.save_mask = save_mask
+        return O, fate, final
+
+    def _finish_saved(self, save_mask, saved_buf):
+        if not save_mask:
+            return None
+        torch = _torch()
+        k = int(self.saved_count.item())
+        if k > saved_buf.numel():
+            raise RuntimeError("saved-index buffer overflow")  # cannot happen: capacity == n
+        return torch.sort(saved_buf[:k]).values
+
+    def propagate_ic(self, ic, first_index=0, want_fate=True, want_final=False, save_mask=0) -> PropagateResult:
+        """ic: torch float64 [6, n] on this device (SoA x,y,z,vx,vy,vz)."""
+        torch = _torch()
+        assert ic.dtype == torch.float64 and ic.dim() == 2 and ic.shape[0] == 6 and ic.is_cuda
+        assert ic.stride(1) == 1
+        n = ic.shape[1]
+        ws = self._workspace(n)
+        saved_buf = torch.empty(n, dtype=torch.int64, device=self.tdev) if save_mask else None
+        O, fate, final = self._outputs(n, want_fate, want_final, save_mask, saved_buf)
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().cmt_propagate_ic(self.dev.handle, n, int(first_index), ic.data_ptr(), ic.stride(0),
+                                                 C.byref(O), ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+        return PropagateResult(self.counters, self.work, fate, final, self._finish_saved(save_mask, saved_buf),
+                               self.flat.fate_names)
+
+    def propagate_philox(self, source: nat.Source, seed: int, first_index: int, n: int, want_fate=False,
+                         want_final=False, save_mask=0) -> PropagateResult:
+        torch = _torch()
+        ws = self._workspace(n)
+        saved_buf = torch.empty(n, dtype=torch.int64, device=self.tdev) if save_mask else None
+        O, fate, final = self._outputs(n, want_fate, want_final, save_mask, saved_buf)
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().cmt_propagate_philox(self.dev.handle, C.byref(source), int(seed) & (2**64 - 1),
+                                                     int(first_index), int(n), C.byref(O), ws.data_ptr(),
+                                                     ws.numel(), _stream_ptr(self.device)))
+        return PropagateResult(self.counters, self.work, fate, final, self._finish_saved(save_mask, saved_buf),
+                               self.flat.fate_names)
+
+    def draw(self, source: nat.Source, seed: int, first_index: int = 0, n: int = 0, index=None):
+        """Materialise source samples as a device tensor [6, n]."""
+        torch = _torch()
+        if index is not None:
+            n = index.numel()
+        ic = torch.empty((6, n), dtype=torch.float64, device=self.tdev)
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().cmt_philox_draw(C.byref(source), int(seed) & (2**64 - 1), int(first_index),
+                                                index.data_ptr() if index is not None else None, n,
+                                                ic.data_ptr(), max(n, 1), _stream_ptr(self.device)))
+        return ic
+
+    def trajectories(self, state, select=None, select_base=0):
+        """Full rows for the molecules in `state` ([6|10, m] device tensor), optionally
+        gathered through `select` (global indices, device int64).  Returns host arrays
+        (rows [k, max_rows, 10] NaN-free up to n_rows[k], n_rows [k], fate [k])."""
+        torch = _torch()
+        n_comp = state.shape[0]
+        k_total = select.numel() if select is not None else state.shape[1]
+        max_rows = self.dev.max_rows
+        per = max(1, min(k_total, ROW_BUDGET_BYTES // (max_rows * nat.CMT_ROW_DOUBLES * 8)))
+        rows_out = np.empty((k_total, max_rows, nat.CMT_ROW_DOUBLES), dtype=np.float64)
+        n_rows_out = np.empty(k_total, dtype=np.int32)
+        fate_out = np.empty(k_total, dtype=np.uint8)
+        for lo in range(0, k_total, per):
+            hi = min(k_total, lo + per)
+            m = hi - lo
+            rows = torch.empty((m, max_rows, nat.CMT_ROW_DOUBLES), dtype=torch.float64, device=self.tdev)
+            n_rows = torch.empty(m, dtype=torch.int32, device=self.tdev)
+            fate = torch.empty(m, dtype=torch.uint8, device=self.tdev)
+            if select is not None:
+                sel_ptr, st_ptr = select[lo:hi].data_ptr(), state.data_ptr()
+            else:
+                sel_ptr, st_ptr = None, state[:, lo:hi].data_ptr()
+            with torch.cuda.device(self.device):
+                nat.check(nat.lib().cmt_trajectories(self.dev.handle, m, st_ptr, n_comp, state.stride(0), sel_ptr,
+                                                     int(select_base), rows.data_ptr(), max_rows,
+                                                     n_rows.data_ptr(), fate.data_ptr(), _stream_ptr(self.device)))
+            rows_out[lo:hi] = rows.cpu().numpy()
+            n_rows_out[lo:hi] = n_rows.cpu().numpy()
+            fate_out[lo:hi] = fate.cpu().numpy()
+        return rows_out, n_rows_out, fate_out
+
+
+# ---------------------------------------------------------------------------
+# distributed helpers (one process per GPU; NCCL on GPUs, gloo in CPU tests)
+# ---------------------------------------------------------------------------
+def dist_info() -> Tuple[int, int]:
+    torch = _torch()
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_rank(), torch.distributed.get_world_size()
+    return 0, 1
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block of the global index range [0,total) owned by `rank`."""
+    base, rem = divmod(int(total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_counts(t):
+    """Sum an int64 tensor over ranks (the Counter merge, trajectory_simulator.py:147-158)."""
+    torch = _torch()
+    if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+    return t

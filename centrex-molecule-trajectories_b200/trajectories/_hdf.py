@@ -1,0 +1,78 @@
+"""HDF5 result layout of the reference, written through h5py.
+
+h5py is an optional dependency (absent from the build image): importing this
+module never needs it, calling a save function does.
+
+  /<run>/counter                        attrs {fate: count}            (trajectory_simulator.py:160-177)
+  /<run>/beamline/<element.name>        attrs class + vars(element)    (apertures.py:56-80)
+  /<run>/position_distribution          attrs class + fields           (distributions.py:122-142)
+  /<run>/velocity_distribution          attrs class + fields           (distributions.py:78-98)
+  /<run>/trajectories/molecule_<i>      datasets x,v,a,t + attrs aperture_hit, alive
+"""
+from __future__ import annotations
+
+
+def h5py():
+    try:
+        import h5py as _h5
+    except ImportError as e:
+        raise ImportError("saving results to HDF5 needs h5py, which is not installed") from e
+    return _h5
+
+
+def save_element(element, filepath, parent_group_path: str) -> None:
+    with h5py().File(filepath, "a") as f:
+        try:
+            path = parent_group_path + "/" + element.name
+            f.create_group(path)
+            f[path].attrs["class"] = type(element).__name__
+            for key, value in vars(element).items():
+                f[path].attrs[key] = value
+        except ValueError:
+            print("Can't save beamline element. Group already exists!")
+
+
+def save_lens(lens, filepath, parent_group_path: str) -> None:
+    # electrostatic_lens.py:145-166: a_interp skipped, state and falsy values stored as repr strings
+    with h5py().File(filepath, "a") as f:
+        path = parent_group_path + "/" + lens.name
+        f.create_group(path)
+        f[path].attrs["class"] = type(lens).__name__
+        for key, value in vars(lens).items():
+            if key == "a_interp":
+                continue
+            if key != "state" and value:
+                f[path].attrs[key] = value
+            else:
+                f[path].attrs[key] = repr(value)
+
+
+def save_beamline(beamline, filepath, run_name: str) -> None:
+    group_path = run_name + "/beamline/"
+    with h5py().File(filepath, "a") as f:
+        f.create_group(group_path)
+    for element in beamline.elements:
+        element.save_to_hdf(filepath, group_path)
+
+
+def save_distribution(dist, filepath, run_name: str, group: str) -> None:
+    with h5py().File(filepath, "a") as f:
+        try:
+            path = run_name + "/" + group
+            f.create_group(path)
+            f[path].attrs["class"] = type(dist).__name__
+            for key, value in vars(dist).items():
+                f[path].attrs[key] = value
+        except ValueError:
+            raise ValueError(f"Can't save {group.replace('_', ' ')}. Group already exists!")
+
+
+def save_counter(counter, filepath, run_name: str) -> None:
+    with h5py().File(filepath, "a") as f:
+        try:
+            path = run_name + "/counter"
+            f.create_group(path)
+            for key, value in counter.counter_dict.items():
+                f[path].attrs[key] = value
+        except ValueError:
+            raise ValueError("Can't save counter. Group already exists!")

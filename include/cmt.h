@@ -1,0 +1,203 @@
+/*
+ * cmt.h -- C ABI of libcmt_b200.so: the B200 (sm_100a) implementation of the
+ * Monte Carlo propagation hot path of otimgren/centrex-molecule-trajectories.
+ *
+ * The reference has no FFI of its own (it is pure Python); its plugin API for
+ * this path is the abstract dataclass `BeamlineElement.propagate_through`
+ * (src/trajectories/beamline_elements/apertures.py:22-54) driven by
+ * `Beamline.propagate_through` (src/trajectories/beamline.py:20-38) inside the
+ * per-molecule loop of `TrajectorySimulator.run_simulation`
+ * (src/trajectories/trajectory_simulator.py:52-78).  Each entry point below
+ * names the reference interface it replaces.  INTEGRATION.md shows the ctypes
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross this boundary;
+ *   - every function returns 0 on success or a negative CMT_E* code and never
+ *     throws; cmt_last_error() returns a thread-local message for the last
+ *     failure on the calling thread;
+ *   - pointers documented "device" are caller-owned device memory on the
+ *     handle's device (e.g. torch tensors' data_ptr()); the *_host entry
+ *     points take host memory and do their own staging;
+ *   - device entry points are asynchronous on `stream` (a cudaStream_t passed
+ *     as void*, NULL = legacy default stream) and never synchronise;
+ *   - a beamline handle is immutable after creation: concurrent launches on
+ *     different streams are safe as long as each uses its own workspace and
+ *     output buffers;
+ *   - all arithmetic is IEEE-754 binary64 in the reference's operation order
+ *     (no fused multiply-add on the path that decides fates).
+ */
+#ifndef CMT_H
+#define CMT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMT_VERSION 100          /* 0.1.0 */
+#define CMT_MAX_ELEMENTS 40      /* element table lives in kernel-parameter constant memory */
+#define CMT_MAX_FATES 64         /* fates are stored as uint8 and selected by a 64-bit mask */
+#define CMT_MAX_TABLES 8
+#define CMT_ROW_DOUBLES 10       /* x,y,z,vx,vy,vz,ax,ay,az,t: one Trajectory row (molecule.py:133-144) */
+
+/* error codes */
+#define CMT_OK 0
+#define CMT_EINVAL (-1)          /* bad argument */
+#define CMT_ECUDA (-2)           /* CUDA runtime error (see cmt_last_error) */
+#define CMT_ENOMEM (-3)          /* workspace too small / allocation failed */
+#define CMT_ENODEV (-4)          /* no usable sm_100 device */
+
+/* element kinds */
+#define CMT_CIRCULAR 0           /* CircularAperture,    apertures.py:83-115  */
+#define CMT_RECTANGULAR 1        /* RectangularAperture, apertures.py:147-189 */
+#define CMT_FIELDPLATES 2        /* FieldPlates,         apertures.py:213-270 */
+#define CMT_LENS 3               /* ElectrostaticLens,   electrostatic_lens.py:23-118 */
+
+/*
+ * One flattened beamline element (replaces a BeamlineElement dataclass
+ * instance; fields follow apertures.py:22-36,157-163,221-225 and
+ * electrostatic_lens.py:29-46).  Elements must be sorted by z0
+ * (beamline.py:40-45).
+ */
+typedef struct cmt_element {
+    int32_t type;      /* CMT_CIRCULAR .. CMT_LENS */
+    int32_t fate;      /* fate id recorded on a hit; lens: id of "Lens entrance" */
+    int32_t fate2;     /* lens only: id of "Inside lens" */
+    int32_t table;     /* lens only: index into the tables given at creation */
+    int32_t n_steps;   /* lens only: int(rint(L/dz)), electrostatic_lens.py:87 */
+    int32_t reserved;
+    double z0, z1;     /* entrance and exit planes, z1 = z0 + L */
+    double x1, x2;     /* rectangular / field plates: open interval in x */
+    double y1, y2;     /* rectangular: open interval in y */
+    double R;          /* circular aperture / lens bore: d/2 (test is sqrt(x^2+y^2) > R about the origin) */
+    double dz;         /* lens only: integration step along z */
+} cmt_element_t;
+
+/* Lens radial-acceleration table a_r(r): what ElectrostaticLens.a_interp holds
+ * (electrostatic_lens.py:32,209): r ascending, linear interpolation. Host memory. */
+typedef struct cmt_table {
+    const double *r;
+    const double *a;
+    int32_t n;
+    int32_t reserved;
+} cmt_table_t;
+
+/* Molecular-beam source (replaces Distribution.draw, distributions.py:69-76,
+ * 112-119,155-162).  Samples come from Philox4x32-10 keyed by `seed` and
+ * indexed by the global molecule index (see DESIGN.md "Source"). */
+#define CMT_POS_DISC 0           /* CeNTREXPositionDistribution: uniform disc of radius p0 */
+#define CMT_POS_GAUSS 1          /* GaussianPositionDistribution: N(0,p0) x N(0,p1) */
+typedef struct cmt_source {
+    int32_t pos_kind;
+    int32_t reserved;
+    double vmean[3];
+    double vsigma[3];
+    double p0, p1;
+    double z;
+} cmt_source_t;
+
+/* Output bundle of a propagation call; every pointer is device memory. */
+typedef struct cmt_outputs {
+    uint8_t *fate;          /* [n] fate id per molecule, or NULL */
+    double *final_state;    /* [10][final_ld] SoA last trajectory row per molecule (x,y,z,vx,vy,vz,ax,ay,az,t), or NULL */
+    int64_t final_ld;       /* leading dimension of final_state (>= n) */
+    int64_t *counters;      /* [n_fates] per-fate counts, ACCUMULATED (Counter, trajectory_simulator.py:106-124); required */
+    int64_t *work;          /* [4] accumulated: ballistic rows, lens RK steps, table out-of-range evaluations, lens entries; or NULL */
+    int64_t *saved_index;   /* [saved_capacity] global indices of molecules whose fate is in save_mask (unordered), or NULL */
+    int64_t *saved_count;   /* [1] accumulated cursor into saved_index (may exceed capacity: then the list is truncated) */
+    int64_t saved_capacity;
+    uint64_t save_mask;     /* bit f set: fate f is an "aperture of interest" (trajectory_simulator.py:75-76) */
+} cmt_outputs_t;
+
+typedef struct cmt_beamline cmt_beamline_t;
+
+/* ---- lifetime ---------------------------------------------------------- */
+
+/* Replaces building a `Beamline` (beamline.py:10-18): copies the element table
+ * and lens tables to `device`, precomputes exact squared-radius thresholds and
+ * table slopes.  fate ids must be < n_fates <= CMT_MAX_FATES. */
+int cmt_beamline_create(const cmt_element_t *elements, int n_elements,
+                        const cmt_table_t *tables, int n_tables,
+                        int n_fates, int fate_detected, double g, int device,
+                        cmt_beamline_t **out);
+void cmt_beamline_destroy(cmt_beamline_t *bl);
+
+/* Rows a full trajectory can have: 1 + sum(N_steps) (molecule.py:115-131 without its 10 spare rows). */
+int cmt_beamline_max_rows(const cmt_beamline_t *bl);
+int cmt_beamline_device(const cmt_beamline_t *bl);
+
+/* Bytes of device scratch a propagation call over up to n_max molecules needs. */
+size_t cmt_workspace_bytes(const cmt_beamline_t *bl, int64_t n_max);
+
+/* ---- the hot path ------------------------------------------------------ */
+
+/* Replaces the per-molecule loop trajectory_simulator.py:62-76 for explicit
+ * initial conditions: molecule i starts at (ic[0..2][i], ic[3..5][i]) with
+ * a=(0,-g,0), t=0 (molecule.py:15-24) and is walked through every element
+ * (beamline.py:20-38).  ic is device memory, SoA [6][ic_ld].  Global index of
+ * molecule i (reported in saved_index) is first_index + i. */
+int cmt_propagate_ic(const cmt_beamline_t *bl, int64_t n, int64_t first_index,
+                     const double *ic, int64_t ic_ld, const cmt_outputs_t *out,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* Same, with initial conditions generated on the device (replaces
+ * vdist.draw/xdist.draw + the loop, trajectory_simulator.py:57-76). */
+int cmt_propagate_philox(const cmt_beamline_t *bl, const cmt_source_t *src, uint64_t seed,
+                         int64_t first_index, int64_t n, const cmt_outputs_t *out,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* Materialise the source's samples: ic[c][j] for global index first_index + j
+ * (index == NULL) or index[j] (device int64).  ic is device memory [6][ic_ld]. */
+int cmt_philox_draw(const cmt_source_t *src, uint64_t seed, int64_t first_index,
+                    const int64_t *index, int64_t n, double *ic, int64_t ic_ld, void *stream);
+
+/* Full trajectories (replaces Trajectory.update bookkeeping, molecule.py:115-167)
+ * for n selected molecules.  state is device memory SoA [n_comp][state_ld] with
+ * n_comp = 6 (x,v; a and t default) or 10 (x,v,a,t: resume from an arbitrary
+ * row, which is what BeamlineElement.propagate_through(molecule) needs).
+ * select (device, optional): molecule j reads column select[j] - select_base.
+ * rows:   [n][max_rows][10] device; rows past n_rows[j] are left untouched.
+ * first_element..: elements [first_element, n_elements) are walked. */
+int cmt_trajectories(const cmt_beamline_t *bl, int64_t n, const double *state, int n_comp,
+                     int64_t state_ld, const int64_t *select, int64_t select_base,
+                     double *rows, int32_t max_rows, int32_t *n_rows, uint8_t *fate,
+                     void *stream);
+
+/* ---- host-buffer convenience (what a non-CUDA host language binds) ------ */
+
+/* ic_host [6][n] (SoA, row-major), fate_host [n] or NULL, final_host [10][n]
+ * or NULL, counters_host [n_fates] (accumulated), work_host [4] or NULL
+ * (accumulated).  Stages through pinned buffers in chunks on two streams so
+ * PCIe copies overlap the kernels; returns after everything has landed. */
+int cmt_run_host_ic(const cmt_beamline_t *bl, int64_t n, const double *ic_host,
+                    uint8_t *fate_host, double *final_host, int64_t *counters_host,
+                    int64_t *work_host);
+
+int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t *src, uint64_t seed,
+                        int64_t first_index, int64_t n, int64_t *counters_host,
+                        int64_t *work_host);
+
+/* ---- diagnostics ------------------------------------------------------- */
+
+/* Per-kernel device time of the calls made on this thread since the last
+ * reset, measured with CUDA events on the launch stream (enable first).
+ * ms[0] = walk kernel (ballistic + aperture tests up to the first lens),
+ * ms[1] = lens kernel (RK integrator + downstream elements), ms[2] = trajectory
+ * kernel, ms[3] = source-only kernel; launches[k] = number of launches. */
+int cmt_timing_enable(int on);
+int cmt_timing_read(double ms[4], int64_t launches[4], int reset);
+
+/* Measured FP64 pipe ceilings on `device` (dependent-chain-free DFMA / DADD
+ * streams), in operations per second; used as roofline denominators. */
+int cmt_fp64_peak(int device, double *dfma_per_s, double *dadd_per_s);
+
+int cmt_version(void);
+const char *cmt_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMT_H */

@@ -94,11 +94,17 @@ static void store_row(orc_mol *m)
     m->n_rows++;
 }
 
+/*
+ * gcc folds pow(x, 2.0) into x*x even without -ffast-math; NumPy's scalar power
+ * really calls libm, so go through a volatile pointer to keep the call.
+ */
+static double (*volatile libm_pow)(double, double) = pow;
+
 /* Molecule.x(delta_t), molecule.py:26-34: `if not delta_t` returns the row. */
 static void pos_after(const orc_mol *m, double dt, double out[3])
 {
     if (dt == 0.0) { out[0] = m->x[0]; out[1] = m->x[1]; out[2] = m->x[2]; return; }
-    double dt2 = pow(dt, 2.0);              /* numpy scalar ** 2 -> libm pow */
+    double dt2 = libm_pow(dt, 2.0);         /* numpy scalar ** 2 -> libm pow */
     for (int c = 0; c < 3; c++)
         out[c] = (m->x[c] + m->v[c] * dt) + (m->a[c] * dt2) / 2;
 }

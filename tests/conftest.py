@@ -1,0 +1,30 @@
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+PKG = ROOT / "centrex-molecule-trajectories_b200"
+for p in (str(ROOT), str(PKG)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return ROOT / "tests" / "golden"
+
+
+@pytest.fixture(scope="session")
+def cuda_lib():
+    """libcmt_b200.so, built in-tree; the GPU tests call through its C ABI."""
+    import __graft_entry__ as ge
+
+    ge.build_cuda()
+    from trajectories import _native
+
+    return _native.lib()

@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures by executing the UNMODIFIED reference source.
+
+Run in the build container only (needs /root/reference; never at test time):
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests or golden vectors, so the
+fixtures are produced by importing /root/reference/src/trajectories through the
+stub packages in oracle/stubs (matplotlib, h5py, hexalattice, centrex_TlF are
+absent from the image) and calling, per molecule,
+
+    m = Molecule(); m.init_trajectory(beamline, x0, v0); beamline.propagate_through(m)
+
+(trajectory_simulator.py:62-69).  The lens acceleration table is injected
+through `ElectrostaticLens.a_interp` (electrostatic_lens.py:32,174) as a scipy
+`interp1d`, built from the build's rigid-rotor Stark model; the table itself is
+stored in the fixture so the tests do not depend on that model.
+
+Outputs (tests/golden/*.npz) record numpy/scipy versions used.
+"""
+from __future__ import annotations
+
+import importlib.util
+import json
+import sys
+import time
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, "/root/reference/src")
+sys.path.insert(0, str(ROOT / "oracle" / "stubs"))
+
+import numpy as np  # noqa: E402
+import scipy  # noqa: E402
+from scipy.interpolate import interp1d  # noqa: E402
+
+from trajectories.beamline import Beamline  # noqa: E402
+from trajectories.beamline_elements.apertures import (  # noqa: E402
+    CircularAperture,
+    FieldPlates,
+    RectangularAperture,
+)
+from trajectories.beamline_elements.electrostatic_lens import ElectrostaticLens  # noqa: E402
+from trajectories.distributions import (  # noqa: E402
+    CeNTREXPositionDistribution,
+    CeNTREXVelocityDistribution,
+    Distribution,
+    GaussianPositionDistribution,
+)
+from trajectories.molecule import Molecule  # noqa: E402
+from trajectories.trajectory_simulator import TrajectorySimulator  # noqa: E402
+
+assert "/root/reference" in sys.modules["trajectories"].__file__
+
+_spec = importlib.util.spec_from_file_location(
+    "_tlf", ROOT / "centrex-molecule-trajectories_b200" / "trajectories" / "_tlf.py"
+)
+_tlf = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_tlf)
+
+M = 0.0254
+
+
+def lens_table(J=2, mJ=0, V=27.6e3, d=1.75 * 0.0254, mass=(204.38 + 19.00) * 1.67e-27):
+    return _tlf.lens_acceleration_table(d, V, mass, J, mJ)
+
+
+def lens_beamline(table):
+    """examples/lens_simulation_beamline.py:21-72"""
+    fourK = CircularAperture(z0=1.7 * M, L=0.25 * M, d=1 * M, name="4K shield")
+    fortyK = CircularAperture(z0=fourK.z1 + 1.25 * M, L=0.25 * M, d=1 * M, name="40K shield")
+    bb = CircularAperture(z0=fortyK.z1 + 2.5 * M, L=0.75 * M, d=4 * M, name="BB exit")
+    lens = ElectrostaticLens(z0=bb.z1 + 33 * M, L=0.6, name="ES lens")
+    lens.a_interp = interp1d(*table)
+    fp = FieldPlates(z0=2.43, L=3.0, w=0.02, name="Field plates")
+    dr = RectangularAperture(z0=fp.z1 + 39.9 * M, L=0.25 * M, name="DR aperture", w=0.018, h=0.03)
+    return Beamline([fourK, fortyK, bb, lens, fp, dr])
+
+
+def apertures_beamline():
+    """The lens beamline without the lens (BASELINE.json configs[0])."""
+    fourK = CircularAperture(z0=1.7 * M, L=0.25 * M, d=1 * M, name="4K shield")
+    fortyK = CircularAperture(z0=fourK.z1 + 1.25 * M, L=0.25 * M, d=1 * M, name="40K shield")
+    bb = CircularAperture(z0=fortyK.z1 + 2.5 * M, L=0.75 * M, d=4 * M, name="BB exit")
+    fp = FieldPlates(z0=2.43, L=3.0, w=0.02, name="Field plates")
+    dr = RectangularAperture(z0=fp.z1 + 39.9 * M, L=0.25 * M, name="DR aperture", w=0.018, h=0.03)
+    return Beamline([fourK, fortyK, bb, fp, dr])
+
+
+def spa_beamline():
+    """examples/SPA/SPA_distributions.py:21-84"""
+    fourK = CircularAperture(z0=1.7 * M, L=0.25 * M, d=1 * M, name="4K shield")
+    fortyK = CircularAperture(z0=fourK.z1 + 1.25 * M, L=0.25 * M, d=1 * M, name="40K shield")
+    bb = CircularAperture(z0=fortyK.z1 + 2.5 * M, L=0.75 * M, d=4 * M, name="BB exit")
+    rc_in = CircularAperture(z0=17.36 * M, L=0.125 * M, d=8e-3, name="RC entrance")
+    rc_out = CircularAperture(z0=(17.36 + 9) * M, L=0.125 * M, d=8e-3, name="RC exit")
+    spa_in = CircularAperture(z0=bb.z1 + 20.5 * M, L=0.375 * M, d=1.75 * M, name="SPA entrance")
+    spa_out = CircularAperture(z0=spa_in.z1 + 9.625 * M, L=0.375 * M, d=1.75 * M, name="SPA exit")
+    dr_in = CircularAperture(z0=(35.37 + 11) * M, L=0.125 * M, d=150e-3, name="DR entrance")
+    laser = RectangularAperture(z0=dr_in.z1 + 3.02 * M, L=2e-3, name="laser", w=0.05, h=0.05)
+    return Beamline([fourK, fortyK, bb, rc_in, rc_out, spa_in, spa_out, dr_in, laser])
+
+
+def fate_names(beamline):
+    names = []
+    for e in beamline.elements:
+        if type(e).__name__ == "ElectrostaticLens":
+            cand = ["Lens entrance", "Inside lens"]
+        else:
+            cand = [e.name]
+        for c in cand:
+            if c not in names:
+                names.append(c)
+    names.append("Detected")
+    return names
+
+
+def run_reference(beamline, ic, rows_per_fate=0):
+    """Per-molecule reference propagation; returns fates, last rows, row counts, sample rows."""
+    names = fate_names(beamline)
+    n = ic.shape[1]
+    fate = np.empty(n, dtype=np.int8)
+    n_rows = np.empty(n, dtype=np.int32)
+    alive = np.empty(n, dtype=np.bool_)
+    fin = np.empty((10, n))
+    kept: dict[int, int] = {}
+    row_idx, row_data = [], []
+    for i in range(n):
+        m = Molecule()
+        m.init_trajectory(beamline, ic[0:3, i].copy(), ic[3:6, i].copy())
+        beamline.propagate_through(m)
+        f = names.index(m.aperture_hit)
+        fate[i] = f
+        alive[i] = m.alive
+        tr = m.trajectory
+        k = tr.x.shape[0]
+        assert tr.v.shape[0] == k and tr.a.shape[0] == k and tr.t.shape[0] == k == tr.n
+        n_rows[i] = k
+        fin[0:3, i], fin[3:6, i], fin[6:9, i], fin[9, i] = tr.x[-1], tr.v[-1], tr.a[-1], tr.t[-1]
+        if kept.get(f, 0) < rows_per_fate:
+            kept[f] = kept.get(f, 0) + 1
+            row_idx.append(i)
+            row_data.append(np.concatenate([tr.x, tr.v, tr.a, tr.t[:, None]], axis=1))
+    out = dict(fate=fate, n_rows=n_rows, alive=alive, fin=fin, fate_names=np.array(names))
+    if row_idx:
+        out["row_idx"] = np.array(row_idx, dtype=np.int64)
+        out["row_off"] = np.cumsum([0] + [r.shape[0] for r in row_data]).astype(np.int64)
+        out["rows"] = np.concatenate(row_data, axis=0)
+    return out
+
+
+def draw_reference(seed, n, vdist, xdist, positions_first=False):
+    np.random.seed(seed)
+    if positions_first:
+        xs = xdist.draw(n)
+        vs = vdist.draw(n)
+    else:  # trajectory_simulator.py:57-58 draws velocities first
+        vs = vdist.draw(n)
+        xs = xdist.draw(n)
+    return np.concatenate([np.asarray(xs, dtype=np.float64), np.asarray(vs, dtype=np.float64)])
+
+
+def edge_ics(table):
+    """Hand-built initial conditions on and next to element edges."""
+    R1 = 1 * M / 2            # 4K shield radius
+    z4k = 1.7 * M             # its entrance plane
+    up = np.nextafter
+    rows = [
+        # x, y, z, vx, vy, vz
+        (0.0, 0.0, 0.00635, 0.0, 0.0, 184.0),               # on axis, no transverse velocity
+        (0.0, 0.0, 0.00635, 0.0, 0.0, 250.0),
+        (0.0, 0.0, 0.00635, 0.0, 0.055, 184.0),             # launched up against gravity
+        (R1, 0.0, z4k, 0.0, 0.0, 184.0),                    # exactly on the 4K edge at dt = 0
+        (up(R1, 1.0), 0.0, z4k, 0.0, 0.0, 184.0),           # one ulp outside
+        (up(R1, 0.0), 0.0, z4k, 0.0, 0.0, 184.0),           # one ulp inside
+        (0.0, R1, z4k, 0.0, 0.0, 184.0),
+        (0.0, -R1, z4k, 0.0, 0.0, 184.0),
+        (0.009, 0.0, 0.00635, 0.0, 0.1, 184.0),             # reaches field plates with vx == 0
+        (0.0099, 0.0, 0.00635, 0.0, 0.1, 184.0),
+        (0.0, 0.0, 0.00635, 0.5, 0.05, 184.0),              # slow drift into the field plates (+x)
+        (0.0, 0.0, 0.00635, -0.5, 0.05, 184.0),             # (-x)
+        (0.0, 0.0, 0.00635, 0.2, 0.2, 150.0),
+        (0.0, 0.0, 0.00635, -0.2, 0.3, 210.0),
+        (0.001, -0.001, 0.00635, 1.5, -1.0, 184.0),         # enters the lens off axis
+        (0.002, 0.002, 0.00635, 3.0, 3.0, 184.0),           # hits the lens bore inside
+        (0.0, 0.0, 0.00635, 4.2, 0.0, 184.0),               # near the lens entrance edge
+        (0.0, 0.0, 0.00635, 0.0, 4.3, 184.0),
+        (0.0, 0.0, 0.00635, 0.3, 0.06, 120.0),              # slow molecule, strong focusing
+        (0.0, 0.0, 0.00635, 0.3, 0.06, 300.0),              # fast molecule, weak focusing
+    ]
+    return np.array(rows, dtype=np.float64).T.copy()
+
+
+class Replay(Distribution):
+    """Hands out consecutive slices of a fixed (3,N) array, like a seeded draw would."""
+
+    def __init__(self, data):
+        self.data, self.pos = data, 0
+
+    def draw(self, n):
+        out = self.data[:, self.pos:self.pos + n]
+        self.pos += n
+        return out
+
+    def save_to_hdf(self, *a, **k):
+        pass
+
+
+def main():
+    t0 = time.time()
+    meta = dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0],
+                reference="/root/reference (otimgren/centrex-molecule-trajectories)")
+    table = lens_table()
+    vstd, xstd = CeNTREXVelocityDistribution(), CeNTREXPositionDistribution()
+
+    # --- standard distributions, lens beamline + apertures-only beamline (configs 1 and 2) ---
+    n_std = 4000
+    for seed in (0, 1, 2):
+        ic = draw_reference(seed, n_std, vstd, xstd)
+        res = run_reference(lens_beamline(table), ic, rows_per_fate=1 if seed == 0 else 0)
+        ap = run_reference(apertures_beamline(), ic)
+        np.savez_compressed(
+            HERE / f"std_seed{seed}.npz", ic=ic, table_r=table[0], table_a=table[1],
+            meta=json.dumps(meta), **{f"lens_{k}": v for k, v in res.items()},
+            **{f"ap_{k}": v for k, v in ap.items()})
+        print(f"std seed {seed}: lens fates {np.bincount(res['fate'])}, ap fates {np.bincount(ap['fate'])}"
+              f"  [{time.time() - t0:.0f}s]", flush=True)
+
+    # --- lens-biased set: sigma_perp = 3 m/s sends most molecules into the lens ---
+    n_lb = 1500
+    ic = draw_reference(123, n_lb, CeNTREXVelocityDistribution(sigmax=3, sigmay=3), xstd,
+                        positions_first=True)
+    res = run_reference(lens_beamline(table), ic, rows_per_fate=3)
+    np.savez_compressed(HERE / "lens_biased.npz", ic=ic, table_r=table[0], table_a=table[1],
+                        meta=json.dumps(meta), **{f"lens_{k}": v for k, v in res.items()})
+    print(f"lens biased: fates {dict(zip(res['fate_names'], np.bincount(res['fate'], minlength=len(res['fate_names']))))}"
+          f"  [{time.time() - t0:.0f}s]", flush=True)
+
+    # --- a second state / voltage (J=3, mJ=0 at 30 kV is field-seeking over part of the range) ---
+    table2 = lens_table(J=1, mJ=1, V=20e3)
+    res = run_reference(lens_beamline(table2), ic[:, :500])
+    np.savez_compressed(HERE / "lens_biased_J1m1_20kV.npz", ic=ic[:, :500], table_r=table2[0],
+                        table_a=table2[1], meta=json.dumps(meta),
+                        **{f"lens_{k}": v for k, v in res.items()})
+    print(f"lens biased J=1 mJ=1 20 kV: fates {np.bincount(res['fate'])}  [{time.time() - t0:.0f}s]", flush=True)
+
+    # --- edge cases ---
+    ic = edge_ics(table)
+    res = run_reference(lens_beamline(table), ic, rows_per_fate=2)
+    ap = run_reference(apertures_beamline(), ic, rows_per_fate=2)
+    np.savez_compressed(HERE / "edges.npz", ic=ic, table_r=table[0], table_a=table[1],
+                        meta=json.dumps(meta), **{f"lens_{k}": v for k, v in res.items()},
+                        **{f"ap_{k}": v for k, v in ap.items()})
+    print(f"edges: lens fates {res['fate']}, ap fates {ap['fate']}", flush=True)
+
+    # --- SPA beamline, Gaussian position source (config 4) ---
+    ic = draw_reference(5, 4000, vstd, GaussianPositionDistribution())
+    # the standard source almost never reaches the laser in 4000 draws: add a collimated batch
+    ic2 = draw_reference(6, 1000, CeNTREXVelocityDistribution(sigmax=1.5, sigmay=1.5),
+                         GaussianPositionDistribution(sigmax=1e-3, sigmay=1e-3))
+    ic = np.concatenate([ic, ic2], axis=1)
+    res = run_reference(spa_beamline(), ic, rows_per_fate=2)
+    np.savez_compressed(HERE / "spa.npz", ic=ic, meta=json.dumps(meta),
+                        **{f"spa_{k}": v for k, v in res.items()})
+    print(f"spa: fates {dict(zip(res['fate_names'], np.bincount(res['fate'], minlength=len(res['fate_names']))))}"
+          f"  [{time.time() - t0:.0f}s]", flush=True)
+
+    # --- run_simulation itself (n_jobs=1) on replayed draws: Counter + saved list semantics ---
+    ic = draw_reference(7, 1300, CeNTREXVelocityDistribution(sigmax=3, sigmay=3), xstd)
+    sim = TrajectorySimulator()
+    bl = lens_beamline(table)
+    aoi = ["Detected", "Inside lens"]
+    sim.run_simulation(bl, "golden", vdist=Replay(ic[3:6]), xdist=Replay(ic[0:3]), N_traj=1234,
+                       apertures_of_interest=aoi, n_jobs=1)
+    saved = sim.result.molecules
+    saved_x0 = np.array([m.trajectory.x[0] for m in saved]).T
+    np.savez_compressed(
+        HERE / "run_simulation.npz", ic=ic, table_r=table[0], table_a=table[1],
+        meta=json.dumps(meta), N_traj=1234, n_jobs=1, aoi=np.array(aoi),
+        counter_keys=np.array(list(sim.counter.counter_dict.keys())),
+        counter_vals=np.array(list(sim.counter.counter_dict.values()), dtype=np.int64),
+        saved_x0=saved_x0, saved_fate=np.array([m.aperture_hit for m in saved]),
+        saved_n_rows=np.array([m.trajectory.x.shape[0] for m in saved], dtype=np.int32),
+        saved_alive=np.array([m.alive for m in saved]),
+        efficiency=sim.counter.calculate_efficiency())
+    print(f"run_simulation: counter {sim.counter.counter_dict}, saved {len(saved)}"
+          f"  [{time.time() - t0:.0f}s]", flush=True)
+
+
+if __name__ == "__main__":
+    main()

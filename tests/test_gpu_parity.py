@@ -1,0 +1,297 @@
+"""Parity of the CUDA path (libcmt_b200.so, through its C ABI) with the CPU oracle
+and with the golden vectors produced by the unmodified reference.
+
+Tolerances (north_star): fates exact; final state 1e-9 relative on ballistic
+segments, 1e-6 through the lens.  What is actually achieved is tighter and is
+asserted: the CUDA path rounds every operation like the reference, except that
+`dt**2` is an exact square on the GPU while NumPy's scalar power goes through
+libm pow() (<= 1 ulp apart in 0.08 % of steps), so final rows agree to ~1e-13.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle
+from tests.beamlines import apertures_beamline, lens_beamline, lens_table, spa_beamline, standard_ics
+
+TIGHT = 1e-12
+
+
+def relerr(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-9))
+
+
+@pytest.fixture(scope="module")
+def torch_cuda(cuda_lib):
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    assert torch.cuda.get_device_capability(0)[0] == 10
+    return torch
+
+
+def gpu_propagate(torch, beamline, ic, **kw):
+    from trajectories import _engine as eng
+
+    prop = eng.Propagator(beamline.elements, 0)
+    prop.reset()
+    res = prop.propagate_ic(torch.from_numpy(np.ascontiguousarray(ic)).cuda(), want_fate=True, want_final=True, **kw)
+    torch.cuda.synchronize()
+    return dict(fate=res.fate.cpu().numpy(), fin=res.final.cpu().numpy(), counters=res.counters.cpu().numpy(),
+                work=res.work.cpu().numpy(), saved=None if res.saved_index is None else res.saved_index.cpu().numpy(),
+                prop=prop)
+
+
+def check_vs_golden(torch, g, prefix, beamline, tol):
+    got = gpu_propagate(torch, beamline, g["ic"])
+    np.testing.assert_array_equal(got["fate"], g[f"{prefix}_fate"])          # exact, no edge band needed
+    assert relerr(got["fin"], g[f"{prefix}_fin"]) < tol
+    np.testing.assert_array_equal(got["counters"], np.bincount(g[f"{prefix}_fate"], minlength=len(got["counters"])))
+    assert got["work"][0] + got["work"][1] == (g[f"{prefix}_n_rows"] - 1).sum()   # every row accounted for
+    return got
+
+
+@pytest.mark.parametrize("name", ["std_seed0", "std_seed1", "std_seed2", "lens_biased", "lens_biased_J1m1_20kV", "edges"])
+def test_golden_lens_beamline(torch_cuda, golden_dir, name):
+    g = np.load(golden_dir / f"{name}.npz")
+    got = check_vs_golden(torch_cuda, g, "lens", lens_beamline((g["table_r"], g["table_a"])), TIGHT)
+    assert got["work"][2] == 0
+
+
+@pytest.mark.parametrize("name", ["std_seed0", "std_seed1", "std_seed2", "edges"])
+def test_golden_apertures_only(torch_cuda, golden_dir, name):
+    g = np.load(golden_dir / f"{name}.npz")
+    check_vs_golden(torch_cuda, g, "ap", apertures_beamline(), TIGHT)
+
+
+def test_golden_spa(torch_cuda, golden_dir):
+    g = np.load(golden_dir / "spa.npz")
+    check_vs_golden(torch_cuda, g, "spa", spa_beamline(), TIGHT)
+
+
+def test_golden_trajectory_rows(torch_cuda, golden_dir):
+    """Saved trajectories row for row (613 rows for a detected molecule)."""
+    from trajectories import _engine as eng
+
+    torch = torch_cuda
+    g = np.load(golden_dir / "lens_biased.npz")
+    bl = lens_beamline((g["table_r"], g["table_a"]))
+    prop = eng.Propagator(bl.elements, 0)
+    idx = g["lens_row_idx"]
+    ic = torch.from_numpy(np.ascontiguousarray(g["ic"][:, idx])).cuda()
+    rows, n_rows, fate = prop.trajectories(ic)
+    off = g["lens_row_off"]
+    for k in range(len(idx)):
+        want = g["lens_rows"][off[k]:off[k + 1]]
+        assert n_rows[k] == want.shape[0] == g["lens_n_rows"][idx[k]]
+        assert fate[k] == g["lens_fate"][idx[k]]
+        assert relerr(rows[k, : n_rows[k]], want) < TIGHT
+    # select path: gather by global index out of the full IC array
+    full = torch.from_numpy(np.ascontiguousarray(g["ic"])).cuda()
+    sel = torch.from_numpy(idx.astype(np.int64) + 1000).cuda()
+    rows2, n_rows2, fate2 = prop.trajectories(full, select=sel, select_base=1000)
+    np.testing.assert_array_equal(n_rows2, n_rows)
+    for k in range(len(idx)):
+        np.testing.assert_array_equal(rows2[k, : n_rows[k]], rows[k, : n_rows[k]])
+
+
+@pytest.mark.parametrize("n,seed,sigma", [(200000, 11, 39.5), (60000, 12, 4.0), (257, 13, 4.0), (1, 14, 4.0), (33, 15, 1.0)])
+def test_oracle_lens_beamline(torch_cuda, n, seed, sigma):
+    """Seeded CeNTREX-shaped ICs at sizes the oracle finishes in seconds; ragged sizes included."""
+    bl = lens_beamline(lens_table())
+    ic = standard_ics(n, seed, sigma)
+    want = oracle.propagate(bl.elements, ic)
+    got = gpu_propagate(torch_cuda, bl, ic)
+    np.testing.assert_array_equal(got["fate"], want["fate"])
+    np.testing.assert_array_equal(got["counters"], want["counters"])
+    np.testing.assert_array_equal(got["work"][:3], want["work"])
+    assert relerr(got["fin"], want["fin"]) < TIGHT
+    same = (got["fin"].view(np.int64) == want["fin"].view(np.int64)).mean()
+    assert same > 0.995          # almost every value is bit-identical (pow() vs exact square)
+
+
+def test_oracle_other_states(torch_cuda):
+    for (J, mJ, V) in [(0, 0, 30e3), (1, 0, 24e3), (2, 2, 34e3), (3, 1, 20e3)]:
+        bl = lens_beamline(lens_table(J=J, mJ=mJ, V=V), V=V)
+        ic = standard_ics(20000, 100 + J, 3.0)
+        want = oracle.propagate(bl.elements, ic)
+        got = gpu_propagate(torch_cuda, bl, ic)
+        np.testing.assert_array_equal(got["fate"], want["fate"])
+        assert relerr(got["fin"], want["fin"]) < TIGHT
+
+
+def test_empty_input(torch_cuda):
+    bl = lens_beamline(lens_table())
+    got = gpu_propagate(torch_cuda, bl, np.empty((6, 0)))
+    assert got["counters"].sum() == 0 and got["fate"].shape == (0,)
+
+
+def test_saved_index(torch_cuda):
+    bl = lens_beamline(lens_table())
+    ic = standard_ics(50000, 21, 3.0)
+    want = oracle.propagate(bl.elements, ic)
+    names = want["fate_names"]
+    mask = (1 << names.index("Detected")) | (1 << names.index("Inside lens"))
+    from trajectories import _engine as eng
+
+    prop = eng.Propagator(bl.elements, 0)
+    prop.reset()
+    res = prop.propagate_ic(torch_cuda.from_numpy(ic).cuda(), first_index=7_000_000_000, save_mask=mask)
+    expect = np.nonzero((want["fate"] == names.index("Detected")) | (want["fate"] == names.index("Inside lens")))[0]
+    np.testing.assert_array_equal(res.saved_index.cpu().numpy(), expect + 7_000_000_000)
+
+
+def test_philox_source(torch_cuda):
+    """Device Philox samples equal the oracle's (integer stream bit-exact; the
+    Box-Muller/sincos transforms differ by ulps between CUDA and glibc)."""
+    from trajectories import _engine as eng
+    from trajectories.distributions import (CeNTREXPositionDistribution, CeNTREXVelocityDistribution,
+                                            GaussianPositionDistribution)
+
+    bl = lens_beamline(lens_table())
+    prop = eng.Propagator(bl.elements, 0)
+    for xdist in (CeNTREXPositionDistribution(), GaussianPositionDistribution()):
+        vdist = CeNTREXVelocityDistribution()
+        src = eng.make_source(vdist, xdist)
+        first = (1 << 33) + 5                       # exercises the high counter word
+        ic = prop.draw(src, seed=0xDEADBEEFCAFE, first_index=first, n=100000).cpu().numpy()
+        want = oracle.draw(oracle.make_source(vdist, xdist), 0xDEADBEEFCAFE, first, 100000)
+        scale = np.array([0.01, 0.01, 1, 39.5, 39.5, 184.0])[:, None]
+        assert np.max(np.abs(ic - want) / scale) < 1e-13
+        idx = torch_cuda.tensor([first + 3, first + 99999, first], dtype=torch_cuda.int64, device="cuda")
+        sub = prop.draw(src, seed=0xDEADBEEFCAFE, index=idx).cpu().numpy()
+        np.testing.assert_array_equal(sub, ic[:, [3, 99999, 0]])
+
+
+def test_philox_run_counts(torch_cuda):
+    """Whole Philox run vs the oracle's run on the same global indices: counts agree
+    except for molecules within rounding of an edge (none expected at this size)."""
+    from trajectories import _engine as eng
+    from trajectories.distributions import CeNTREXPositionDistribution, CeNTREXVelocityDistribution
+
+    bl = lens_beamline(lens_table())
+    vdist, xdist = CeNTREXVelocityDistribution(), CeNTREXPositionDistribution()
+    n = 400000
+    want = oracle.run(bl.elements, oracle.make_source(vdist, xdist), seed=5, first=1000, n=n)
+    prop = eng.Propagator(bl.elements, 0)
+    prop.reset()
+    res = prop.propagate_philox(eng.make_source(vdist, xdist), 5, 1000, n, want_fate=True)
+    got = res.counters.cpu().numpy()
+    assert got.sum() == n
+    assert np.abs(got - want["counters"]).sum() <= 2
+    # sharding invariance: two half-ranges give the same fates as one launch
+    fate_full = res.fate.cpu().numpy()
+    prop.reset()
+    a = prop.propagate_philox(eng.make_source(vdist, xdist), 5, 1000, n // 2, want_fate=True).fate.cpu().numpy()
+    b = prop.propagate_philox(eng.make_source(vdist, xdist), 5, 1000 + n // 2, n - n // 2, want_fate=True).fate.cpu().numpy()
+    np.testing.assert_array_equal(np.concatenate([a, b]), fate_full)
+    np.testing.assert_array_equal(prop.counters.cpu().numpy(), got)
+
+
+def test_host_buffer_entry(torch_cuda, cuda_lib):
+    """cmt_run_host_ic: plain host pointers in, fates/final rows/counters out."""
+    import ctypes as C
+    from trajectories import _engine as eng
+
+    bl = lens_beamline(lens_table())
+    n = (1 << 21) + 12345                             # more than one staging chunk, ragged tail
+    ic = standard_ics(n, 31)
+    prop = eng.Propagator(bl.elements, 0)
+    fate = np.empty(n, dtype=np.uint8)
+    fin = np.empty((10, n))
+    counters = np.zeros(len(prop.flat.fate_names), dtype=np.int64)
+    work = np.zeros(4, dtype=np.int64)
+    rc = cuda_lib.cmt_run_host_ic(prop.dev.handle, n, ic.ctypes.data, fate.ctypes.data, fin.ctypes.data,
+                                  counters.ctypes.data, work.ctypes.data)
+    assert rc == 0, cuda_lib.cmt_last_error()
+    want = oracle.propagate(bl.elements, ic)
+    np.testing.assert_array_equal(fate, want["fate"])
+    np.testing.assert_array_equal(counters, want["counters"])
+    np.testing.assert_array_equal(work[:3], want["work"])
+    assert relerr(fin, want["fin"]) < TIGHT
+
+
+def test_run_simulation_golden(torch_cuda, golden_dir):
+    """TrajectorySimulator.run_simulation on replayed draws == the reference's own run."""
+    from trajectories.distributions import Distribution
+    from trajectories.trajectory_simulator import TrajectorySimulator
+
+    g = np.load(golden_dir / "run_simulation.npz")
+
+    class Replay(Distribution):
+        def __init__(self, data):
+            self.data, self.pos = data, 0
+
+        def draw(self, n):
+            out = self.data[:, self.pos:self.pos + n]
+            self.pos += n
+            return out
+
+        def save_to_hdf(self, *a, **k):
+            pass
+
+    bl = lens_beamline((g["table_r"], g["table_a"]))
+    sim = TrajectorySimulator()
+    sim.run_simulation(bl, "golden", vdist=Replay(g["ic"][3:6]), xdist=Replay(g["ic"][0:3]),
+                       N_traj=int(g["N_traj"]), apertures_of_interest=list(g["aoi"]), n_jobs=int(g["n_jobs"]))
+    want = dict(zip(g["counter_keys"].tolist(), g["counter_vals"].tolist()))
+    assert sim.counter.counter_dict == want
+    assert sim.counter.calculate_efficiency() == float(g["efficiency"])
+    saved = sim.result.molecules
+    assert len(saved) == len(g["saved_fate"])
+    assert [m.aperture_hit for m in saved] == g["saved_fate"].tolist()
+    assert [m.alive for m in saved] == g["saved_alive"].tolist()
+    assert [m.trajectory.x.shape[0] for m in saved] == g["saved_n_rows"].tolist()
+    np.testing.assert_array_equal(np.array([m.trajectory.x[0] for m in saved]).T, g["saved_x0"])
+    assert sim.results["golden"].counter is sim.counter
+    m = saved[0]
+    assert m.trajectory.x.shape[1] == 3 and m.trajectory.v.shape == m.trajectory.a.shape == m.trajectory.x.shape
+    assert m.trajectory.t.shape == (m.trajectory.x.shape[0],) and m.trajectory.n == m.trajectory.x.shape[0]
+
+
+def test_run_simulation_philox(torch_cuda):
+    from trajectories.trajectory_simulator import TrajectorySimulator
+
+    bl = lens_beamline(lens_table())
+    sim = TrajectorySimulator(seed=3)
+    sim.run_simulation(bl, "r", N_traj=1_000_050, apertures_of_interest=["Detected"], n_jobs=10)
+    c = sim.counter.counter_dict
+    assert sum(c.values()) == 1_000_000                       # remainder dropped like the reference
+    assert abs(c["4K shield"] / 1e6 - 0.490) < 0.005 and abs(c["40K shield"] / 1e6 - 0.292) < 0.005
+    assert abs(c["Lens entrance"] / 1e6 - 0.212) < 0.005
+    assert len(sim.result.molecules) == c.get("Detected", 0)
+    for m in sim.result.molecules:
+        assert m.alive and m.aperture_hit == "Detected" and m.trajectory.x.shape == (613, 3)
+    sim2 = TrajectorySimulator(seed=3)
+    sim2.run_simulation(bl, "r", N_traj=1_000_050, apertures_of_interest=[], n_jobs=10)
+    assert sim2.counter.counter_dict == c                      # same seed, same run
+
+
+def test_plugin_single_molecule(torch_cuda, golden_dir):
+    """Beamline.propagate_through(molecule) and element.propagate_through(molecule)."""
+    from trajectories.molecule import Molecule
+
+    g = np.load(golden_dir / "lens_biased.npz")
+    bl = lens_beamline((g["table_r"], g["table_a"]))
+    names = list(g["lens_fate_names"])
+    off = g["lens_row_off"]
+    for k in (0, 5, len(g["lens_row_idx"]) - 1):
+        i = g["lens_row_idx"][k]
+        want = g["lens_rows"][off[k]:off[k + 1]]
+        m = Molecule()
+        m.init_trajectory(bl, g["ic"][0:3, i], g["ic"][3:6, i])
+        bl.propagate_through(m)
+        assert m.aperture_hit == names[g["lens_fate"][i]] and m.alive == bool(g["lens_alive"][i])
+        got = np.concatenate([m.trajectory.x, m.trajectory.v, m.trajectory.a, m.trajectory.t[:, None]], axis=1)
+        assert got.shape == want.shape and relerr(got, want) < TIGHT
+        # element by element, as Beamline.propagate_through does in the reference
+        m2 = Molecule()
+        m2.init_trajectory(bl, g["ic"][0:3, i], g["ic"][3:6, i])
+        for e in bl.elements:
+            e.propagate_through(m2)
+            if not m2.alive:
+                break
+        m2.trajectory.drop_nans()
+        got2 = np.concatenate([m2.trajectory.x, m2.trajectory.v, m2.trajectory.a, m2.trajectory.t[:, None]], axis=1)
+        np.testing.assert_array_equal(got2, got)

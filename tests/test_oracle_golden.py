@@ -1,0 +1,106 @@
+"""The CPU oracle (oracle/cmt_oracle.c) against the golden vectors produced by
+executing the unmodified reference (tests/golden/make_golden.py).  Bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.beamlines import apertures_beamline, lens_beamline, spa_beamline
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.int64)
+
+
+def check_case(g, prefix, beamline):
+    res = oracle.propagate(beamline.elements, g["ic"], want_rows=True)
+    assert res["fate_names"] == list(g[f"{prefix}_fate_names"])
+    np.testing.assert_array_equal(res["fate"], g[f"{prefix}_fate"])
+    np.testing.assert_array_equal(res["n_rows"], g[f"{prefix}_n_rows"])
+    np.testing.assert_array_equal(bits(res["fin"]), bits(g[f"{prefix}_fin"]))       # bit for bit
+    detected = res["fate"] == res["fate_names"].index("Detected")
+    np.testing.assert_array_equal(detected, g[f"{prefix}_alive"])
+    if f"{prefix}_rows" in g:
+        off = g[f"{prefix}_row_off"]
+        for k, i in enumerate(g[f"{prefix}_row_idx"]):
+            want = g[f"{prefix}_rows"][off[k]:off[k + 1]]
+            got = res["rows"][i, : want.shape[0]]
+            np.testing.assert_array_equal(bits(got), bits(want))
+            assert np.isnan(res["rows"][i, want.shape[0]:]).all()
+    counts = np.bincount(g[f"{prefix}_fate"], minlength=len(res["fate_names"]))
+    np.testing.assert_array_equal(res["counters"], counts)
+    return res
+
+
+@pytest.mark.parametrize("name", ["std_seed0", "std_seed1", "std_seed2", "lens_biased", "lens_biased_J1m1_20kV", "edges"])
+def test_lens_beamline(golden_dir, name):
+    g = np.load(golden_dir / f"{name}.npz")
+    res = check_case(g, "lens", lens_beamline((g["table_r"], g["table_a"])))
+    assert res["work"][2] == 0   # no force evaluation outside the table
+
+
+@pytest.mark.parametrize("name", ["std_seed0", "std_seed1", "std_seed2", "edges"])
+def test_apertures_only(golden_dir, name):
+    g = np.load(golden_dir / f"{name}.npz")
+    check_case(g, "ap", apertures_beamline())
+
+
+def test_spa(golden_dir):
+    g = np.load(golden_dir / "spa.npz")
+    res = check_case(g, "spa", spa_beamline())
+    det = res["fate"] == res["fate_names"].index("Detected")
+    assert (res["n_rows"][det] == 19).all()       # 1 + 2 x 9 rows, SURVEY.md 3.4
+
+
+def test_row_counts(golden_dir):
+    g = np.load(golden_dir / "lens_biased.npz")
+    names = list(g["lens_fate_names"])
+    det = g["lens_fate"] == names.index("Detected")
+    assert det.sum() > 10 and (g["lens_n_rows"][det] == 613).all()
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for philox4x32-10."""
+    kat = [
+        ([0, 0, 0, 0], [0, 0], "6627e8d5 e169c58d bc57ac4c 9b00dbd8"),
+        ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, "408f276d 41c83b0e a20bc7c6 6d5451fd"),
+        ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+         "d16cfe09 94fdcceb 5001e420 24126ea1"),
+    ]
+    for ctr, key, want in kat:
+        got = " ".join(f"{v:08x}" for v in oracle.philox4x32_10(ctr, key))
+        assert got == want
+
+
+def test_source_statistics():
+    from trajectories.distributions import (CeNTREXPositionDistribution, CeNTREXVelocityDistribution,
+                                            GaussianPositionDistribution)
+
+    n = 400000
+    src = oracle.make_source(CeNTREXVelocityDistribution(), CeNTREXPositionDistribution())
+    ic = oracle.draw(src, seed=1, first=0, n=n)
+    assert abs(ic[3].mean()) < 0.3 and abs(ic[3].std() - 39.5) < 0.2
+    assert abs(ic[4].std() - 39.5) < 0.2 and abs(ic[5].mean() - 184) < 0.1 and abs(ic[5].std() - 16) < 0.1
+    r = np.hypot(ic[0], ic[1])
+    assert r.max() <= 0.01 and abs((r ** 2).mean() - 0.01 ** 2 / 2) < 1e-6    # uniform on the disc
+    assert (ic[2] == 0.25 * 0.0254).all()
+    # index-addressed: any sub-range reproduces the same samples
+    np.testing.assert_array_equal(oracle.draw(src, 1, 1000, 50), ic[:, 1000:1050])
+    src = oracle.make_source(CeNTREXVelocityDistribution(), GaussianPositionDistribution())
+    ic = oracle.draw(src, seed=2, first=0, n=n)
+    s = 0.25 * 25.4 / 5 * 3.8e-3
+    assert abs(ic[0].std() - s) < 3e-5 and abs(ic[1].std() - s) < 3e-5
+    assert abs(np.corrcoef(ic[0], ic[1])[0, 1]) < 0.01 and abs(np.corrcoef(ic[3], ic[5])[0, 1]) < 0.01
+
+
+def test_oracle_run_matches_draw_plus_propagate(golden_dir):
+    from trajectories.distributions import CeNTREXPositionDistribution, CeNTREXVelocityDistribution
+
+    g = np.load(golden_dir / "std_seed0.npz")
+    bl = lens_beamline((g["table_r"], g["table_a"]))
+    src = oracle.make_source(CeNTREXVelocityDistribution(sigmax=5, sigmay=5), CeNTREXPositionDistribution())
+    n = 30000
+    a = oracle.run(bl.elements, src, seed=9, first=123, n=n)
+    b = oracle.propagate(bl.elements, oracle.draw(src, 9, 123, n))
+    np.testing.assert_array_equal(a["counters"], b["counters"])
+    np.testing.assert_array_equal(a["work"], b["work"])
+    assert a["counters"].sum() == n
