@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- molecules/s through the CeNTREX beamline (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is one pass of the hot path over one batch of synthetic molecules:
+BASELINE.json configs[1], the full CeNTREX beamline of
+examples/lens_simulation_beamline.py with the ElectrostaticLens (J=2 Stark
+curve), 1e7 molecules per GPU per step (weak scaling: the molecules of a run
+are independent and are sharded over ranks by global index).
+
+  value      device-resident initial conditions (SoA FP64 in HBM, 480 MB per
+             step > 126 MB L2, so no flush is needed) -> fates + Counter;
+             CUDA events around the K steps, max over ranks.
+  e2e        the same batch through the C ABI's host-buffer entry point
+             (cmt_run_host_ic): pinned host ICs -> H2D -> kernels -> fates and
+             Counter D2H, all inside the timed region.
+  e2e_philox the run_simulation default path: Philox source on the device, only
+             the Counter comes back (reported beside e2e, not instead of it).
+  roofline   the dominant kernel (lens integrator) against the FP64 pipe, and
+             roofline_walk for the ballistic/aperture kernel against HBM.
+  cpu_baseline / --impl reference: the CPU oracle port (oracle/cmt_oracle.c,
+             OpenMP over all host cores) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+PKG = ROOT / "centrex-molecule-trajectories_b200"
+for p in (str(ROOT), str(PKG)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "molecules/s through CeNTREX beamline"
+UNIT = "molecules/s"
+WORKLOAD = ("configs[1]: examples/lens_simulation_beamline.py full CeNTREX beamline with ElectrostaticLens, "
+            "J=2 mJ=0 Stark curve at 27.6 kV, CeNTREX velocity/position distributions")
+# algorithmic work per unit
+FLOP_PER_ROW = 30      # one ballistic step + hit test
+FLOP_PER_STEP = 162    # one lens RK step (4 force evaluations)
+BYTES_PER_MOLECULE = 49  # IC replay: 6 x 8 B read + 1 B fate written
+
+
+def build_workload():
+    from trajectories.centrex import lens_beamline, lens_table
+    from trajectories.distributions import CeNTREXPositionDistribution, CeNTREXVelocityDistribution
+
+    bl = lens_beamline(lens_table())
+    return bl, CeNTREXVelocityDistribution(), CeNTREXPositionDistribution()
+
+
+# ---------------------------------------------------------------------------
+# CPU arm (oracle port)
+# ---------------------------------------------------------------------------
+def cpu_rate(bl, vdist, xdist, target_s: float, seed: int = 1):
+    """molecules/s of the oracle port on all host cores over ~target_s seconds of work."""
+    from oracle import oracle
+
+    src = oracle.make_source(vdist, xdist)
+    flat = oracle.flatten(bl.elements)
+    threads = oracle.max_threads()
+    n = 200_000
+    t0 = time.perf_counter()
+    oracle.run(flat, src, seed, 0, n)
+    probe = time.perf_counter() - t0
+    n = int(max(n, min(2e9, n * target_s / max(probe, 1e-3))))
+    t0 = time.perf_counter()
+    res = oracle.run(flat, src, seed, 10_000_000_000, n)
+    dt = time.perf_counter() - t0
+    return dict(value=n / dt, n=n, seconds=dt, cores=threads, counters=res["counters"].tolist())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle
+
+    bl, vdist, xdist = build_workload()
+    src = oracle.make_source(vdist, xdist)
+    flat = oracle.flatten(bl.elements)
+    threads = oracle.max_threads()
+    t0 = time.perf_counter()
+    oracle.run(flat, src, 1, 0, 200_000)
+    probe = time.perf_counter() - t0
+    # each step a bounded sample: ~2.5 s of host work, so K+W steps end within a few minutes
+    per_step = int(max(200_000, 200_000 * 2.5 / max(probe, 1e-3)))
+    for w in range(args.warmup):
+        oracle.run(flat, src, 1, (w + 1) * per_step, per_step)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        oracle.run(flat, src, 1, (args.warmup + k + 1) * per_step, per_step)
+    dt = time.perf_counter() - t0
+    value = args.steps * per_step / dt
+    sample = f"{per_step} molecules per step (bounded sample of the 1e7-molecule step), Philox source + propagation + Counter"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "molecules_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while a region runs."""
+
+    REASONS = {
+        0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+        0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        if not self.nv:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            try:
+                bits = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                bits = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if bits & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def start(self):
+        def loop():
+            while not self._stop.is_set():
+                self.sample()
+                self._stop.wait(0.02)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from trajectories import _engine as eng
+    from trajectories import _native as nat
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the propagation path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = nat.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    bl, vdist, xdist = build_workload()
+    prop = eng.Propagator(bl.elements, local)
+    source = eng.make_source(vdist, xdist)
+    n = int(args.molecules)
+    seed = 2026
+    first = rank * n                               # this rank's block of the global index range
+    ic = prop.draw(source, seed, first, n)         # synthetic CeNTREX-shaped ICs, resident in HBM
+    torch.cuda.synchronize()
+
+    def step():
+        res = prop.propagate_ic(ic, first_index=first, want_fate=True)
+        if world > 1:
+            dist.all_reduce(prop.counters)         # the Counter merge (tiny, NCCL over NVLink)
+        return res
+
+    # ---- value: device-resident inputs ----
+    for _ in range(max(args.warmup, 3)):
+        prop.reset()
+        step()
+    barrier()
+    lib.cmt_timing_enable(1)
+    lib.cmt_timing_read(None, None, 1)
+    sampler = ClockSampler(local)
+    prop.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record()
+    for _ in range(args.steps):
+        prop.reset()
+        res = step()
+    e1.record()
+    while not e1.query():
+        time.sleep(0.002)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_k = (C.c_double * 4)()
+    n_k = (C.c_int64 * 4)()
+    lib.cmt_timing_read(ms_k, n_k, 1)
+    lib.cmt_timing_enable(0)
+    counters = res.counters.cpu().numpy()
+    work = res.work.cpu().numpy()                  # of the last step (reset each step)
+    value = world * n * args.steps / (ms * 1e-3)
+
+    # ---- roofline ----
+    dfma, dadd = C.c_double(), C.c_double()
+    nat.check(lib.cmt_fp64_peak(local, C.byref(dfma), C.byref(dadd)))
+    peaks = {}
+    mp = ROOT / "MEASURED_PEAKS.json"
+    if mp.exists():
+        peaks = json.loads(mp.read_text())
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    walk_ms = ms_k[0] / max(n_k[0], 1)
+    lens_ms = ms_k[1] / max(n_k[1], 1)
+    # rows committed by the walk kernel = all rows of molecules retired there + entrance rows of survivors;
+    # the split is not needed for the totals: report the whole-step algorithmic flop and each kernel's share
+    flop_lens = FLOP_PER_STEP * float(work[1])
+    flop_rows = FLOP_PER_ROW * float(work[0])
+    lens_tflops = flop_lens / (lens_ms * 1e-3) / 1e12 if lens_ms > 0 else None
+    fp64_peak_tflops = 2 * dfma.value / 1e12       # FMA = 2 flop
+    roofline = {
+        "kernel": "lens_kernel", "bound": "fp64", "achieved": lens_tflops, "peak": fp64_peak_tflops,
+        "unit": "TFLOP/s", "frac": (lens_tflops / fp64_peak_tflops) if lens_tflops else None, "traffic": None,
+        "peak_source": "measured live: cmt_fp64_peak DFMA stream (no FP64 figure in MEASURED_PEAKS.json)",
+        "algorithmic_flop_per_launch": flop_lens, "avg_launch_ms": lens_ms,
+        "share_of_step": lens_ms / (ms / args.steps) if ms > 0 else None,
+        "dadd_peak_tops": dadd.value / 1e12,
+    }
+    walk_gbs = BYTES_PER_MOLECULE * n / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else None
+    roofline_walk = {
+        "kernel": "walk_kernel<ic>", "bound": "hbm", "achieved": walk_gbs, "peak": hbm_peak, "unit": "GB/s",
+        "frac": (walk_gbs / hbm_peak) if walk_gbs else None, "traffic": None, "peak_source": hbm_src,
+        "algorithmic_bytes_per_launch": BYTES_PER_MOLECULE * n, "avg_launch_ms": walk_ms,
+        "share_of_step": walk_ms / (ms / args.steps) if ms > 0 else None,
+        "algorithmic_flop_per_launch": flop_rows,
+    }
+
+    # ---- e2e: host buffers through the C ABI ----
+    ic_host = torch.empty((6, n), dtype=torch.float64, pin_memory=True)
+    ic_host.copy_(ic)
+    fate_host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    cnt_host = np.zeros(len(prop.flat.fate_names), dtype=np.int64)
+    work_host = np.zeros(4, dtype=np.int64)
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        cnt_host[:] = 0
+        nat.check(lib.cmt_run_host_ic(prop.dev.handle, n, ic_host.data_ptr(), fate_host.data_ptr(), None,
+                                      cnt_host.ctypes.data, work_host.ctypes.data))
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * n * args.steps / e2e_s
+    e2e_ok = bool((cnt_host == counters).all()) if world == 1 else None
+
+    # ---- e2e_philox: the run_simulation default path (device source, Counter back) ----
+    def philox_step():
+        cnt_host[:] = 0
+        nat.check(lib.cmt_run_host_philox(prop.dev.handle, C.byref(source), seed, first, n, cnt_host.ctypes.data,
+                                          work_host.ctypes.data))
+
+    for _ in range(3):
+        philox_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        philox_step()
+    torch.cuda.synchronize()
+    ph_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    philox_value = world * n * args.steps / ph_s
+    philox_same = bool((cnt_host == counters).all()) if world == 1 else None
+
+    # ---- CPU baseline (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_rate(bl, vdist, xdist, target_s=12.0)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": f"{r['n']} molecules of the same workload ({r['seconds']:.1f} s): Philox source + propagation + Counter, oracle/cmt_oracle.c with OpenMP"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "molecules_per_step_per_gpu": n,
+                       "inputs": "SoA FP64 initial conditions resident in HBM (480 MB per 1e7 molecules, larger than the 126 MB L2: no flush needed)",
+                       "outputs": "fate byte per molecule + per-fate Counter (+ NCCL all-reduce of the Counter when n_gpus > 1)",
+                       "sharding": "independent molecules, contiguous global-index block per rank"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": n + 8 * (len(cnt_host) + 4),
+                    "path": "cmt_run_host_ic: pinned host ICs -> H2D (2 streams, 2^21-molecule chunks) -> kernels -> fates + Counter D2H",
+                    "counters_match_device_run": e2e_ok},
+            "e2e_philox": {"value": philox_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * (len(cnt_host) + 4),
+                           "path": "cmt_run_host_philox (run_simulation default): Philox4x32-10 source on device, Counter D2H",
+                           "counters_match_device_run": philox_same},
+            "gpu_launches": int(n_k[0] + n_k[1]),
+            "roofline": roofline, "roofline_walk": roofline_walk,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "counters": dict(zip(prop.flat.fate_names, counters.tolist())),
+            "work_per_step": {"ballistic_rows": int(work[0]), "lens_rk_steps": int(work[1]),
+                              "table_out_of_range": int(work[2]), "lens_entries": int(work[3])},
+            "kernel_ms_per_step": {"walk": walk_ms, "lens": lens_ms},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--molecules", type=float, default=1e7, help="molecules per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -241,7 +241,6 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
                 lens_step(tb, lc, m, P.g, oob);
                 oob_total += oob;
                 ++steps_total;
-                ++rows_total;
                 ++step;
                 if (outside_radius(m, E.p[0])) fate = E.fate2;          // "Inside lens"
                 else if (step >= E.n_steps) {

@@ -272,7 +272,7 @@ class Propagator:
         """ic: torch float64 [6, n] on this device (SoA x,y,z,vx,vy,vz)."""
         torch = _torch()
         assert ic.dtype == torch.float64 and ic.dim() == 2 and ic.shape[0] == 6 and ic.is_cuda
-        assert ic.stride(1) == 1
+        assert ic.shape[1] == 0 or ic.stride(1) == 1
         n = ic.shape[1]
         ws = self._workspace(n)
         saved_buf = torch.empty(n, dtype=torch.int64, device=self.tdev) if save_mask else None
