@@ -39,6 +39,14 @@ static int fail(int code, const char *fmt, ...)
     } while (0)
 
 extern "C" const char *cmt_last_error(void) { return g_err; }
+
+static int g_debug_flags = 0;
+extern "C" int cmt_debug_flags(int flags)
+{
+    const int old = g_debug_flags;
+    if (flags >= 0) g_debug_flags = flags;
+    return old;
+}
 extern "C" int cmt_version(void) { return CMT_VERSION; }
 
 // ---------------------------------------------------------------------------
@@ -49,7 +57,7 @@ struct cmt_beamline {
     int device;
     int max_rows;
     int n_sm;
-    double *d_tab;      // [3][tab_total]
+    double4 *d_tab;     // [tab_total]: (r_j, a_j, slope_j, r_{j+1})
     size_t tab_bytes;   // dynamic shared memory the lens/trajectory kernels need
 };
 
@@ -119,6 +127,7 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
     P.first_lens = n_elements;
     P.g = g;
     P.tab_total = tab_total;
+    P.flags = g_debug_flags;
     bl->device = device;
     bl->n_sm = prop.multiProcessorCount;
     bl->max_rows = 1;
@@ -167,19 +176,23 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
         }
     }
 
-    bl->tab_bytes = (size_t)3 * tab_total * sizeof(double);
+    bl->tab_bytes = (size_t)tab_total * sizeof(double4);
     if (tab_total > 0) {
-        std::vector<double> h((size_t)3 * tab_total, 0.0);
+        std::vector<double4> h((size_t)tab_total);
         for (int t = 0; t < n_tables; ++t) {
             const cmt_table_t &tb = tables[t];
             for (int i = 0; i < tb.n; ++i) {
-                h[tab_off[t] + i] = tb.r[i];
-                h[(size_t)tab_total + tab_off[t] + i] = tb.a[i];
+                double4 &e = h[tab_off[t] + i];
+                e.x = tb.r[i];
+                e.y = tb.a[i];
+                e.z = 0.0;
+                e.w = std::numeric_limits<double>::infinity();
                 if (i + 1 < tb.n) {
                     // np.interp: slope = (fp[j+1]-fp[j]) / (xp[j+1]-xp[j]); same IEEE ops here
                     volatile double num = tb.a[i + 1] - tb.a[i];
                     volatile double den = tb.r[i + 1] - tb.r[i];
-                    h[(size_t)2 * tab_total + tab_off[t] + i] = num / den;
+                    e.z = num / den;
+                    e.w = tb.r[i + 1];
                 }
             }
         }
@@ -553,6 +566,27 @@ extern "C" int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t 
         if (rc) return rc;
     }
     return pipe_collect(p, bl, counters_host, work_host);
+}
+
+// ---------------------------------------------------------------------------
+// arithmetic self-test
+// ---------------------------------------------------------------------------
+extern "C" int cmt_selftest(int device, int64_t n, uint64_t seed, int mode, int64_t out[5])
+{
+    if (!out || n < 0 || mode < 0 || mode > 2) return fail(CMT_EINVAL, "bad selftest arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    unsigned long long *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 5 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(d, 0, 5 * sizeof(unsigned long long)));
+    selftest_kernel<<<148 * 8, 256>>>(n, seed, mode, d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    unsigned long long h[5] = {0, 0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(CMT_ECUDA, "selftest failed: %s", cudaGetErrorString(e));
+    for (int k = 0; k < 5; ++k) out[k] = (int64_t)h[k];
+    return CMT_OK;
 }
 
 // ---------------------------------------------------------------------------

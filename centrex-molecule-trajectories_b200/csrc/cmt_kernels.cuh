@@ -26,6 +26,7 @@ namespace cmt {
 constexpr int WALK_THREADS = 256;
 constexpr int LENS_THREADS = 128;
 constexpr int TRAJ_THREADS = 64;
+constexpr int LENS_BURST = 4;       // RK steps per state-machine turn
 constexpr int QUEUE_COMPONENTS = 8;  // x,y,z,vx,vy,vz,t + global index bits
 
 struct Queue {
@@ -136,7 +137,7 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
         } else {
             m.x = m.y = m.z = m.vx = m.vy = 0.0; m.vz = 1.0;
         }
-        m.t = 0.0; m.ax = 0.0; m.ay = -P.g;
+        mol_begin(m, P.g);
 
         CountRows rec;
         int fate = -1;
@@ -181,23 +182,27 @@ __global__ void __launch_bounds__(LENS_THREADS)
 lens_kernel(const __grid_constant__ Params P, int64_t first_index,
             const __grid_constant__ cmt_outputs_t O, Queue Q)
 {
-    extern __shared__ double smem_tab[];
+    extern __shared__ double4 smem_tab[];
     __shared__ BlockAcc acc;
-    for (int i = threadIdx.x; i < 3 * P.tab_total; i += blockDim.x) smem_tab[i] = P.tab[i];
+    for (int i = threadIdx.x; i < P.tab_total; i += blockDim.x) smem_tab[i] = P.tab[i];
     block_acc_init(acc);
 
     const unsigned long long count = min(*Q.count, (unsigned long long)Q.cap);
+    const bool reference_math = (P.flags & CMT_FLAG_REFERENCE_MATH) != 0;
+    const double r6 = rcp_refined(6.0);
     unsigned rows_total = 0, steps_total = 0, oob_total = 0;
 
     Mol m;
-    m.x = m.y = m.z = m.vx = m.vy = m.t = m.ax = m.ay = 0.0; m.vz = 1.0;
+    m.x = m.y = m.z = m.vx = m.vy = m.t = m.ax = m.ay = 0.0; m.vz = 1.0; m.rvz = 1.0;
     int64_t local = 0;
-    int e = 0;          // element being processed
-    int step = -1;      // >= 0: RK steps already taken inside lens e
+    int e = 0;              // element being processed
+    int step = -1;          // >= 0: RK steps already taken inside lens e
+    int n_steps = 0;        // of lens e
+    double bore_T = 0.0;    // of lens e
     bool have = false;
     bool drained = false;   // warp-uniform: the queue has nothing left
     Table tb;
-    tb.r = tb.a = tb.s = smem_tab; tb.n = 2; tb.inv_h = 0.0;
+    tb.t = smem_tab; tb.n = 2; tb.inv_h = 0.0;
     LensConsts lc;
     lc.dt = 0.0; lc.zinc = 0.0;
 
@@ -216,13 +221,15 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
                         const double *q = Q.q + k;
                         m.x = q[0 * Q.cap];  m.y = q[1 * Q.cap];  m.z = q[2 * Q.cap];
                         m.vx = q[3 * Q.cap]; m.vy = q[4 * Q.cap]; m.vz = q[5 * Q.cap];
-                        m.t = q[6 * Q.cap];
+                        const double t = q[6 * Q.cap];
                         local = __double_as_longlong(q[7 * Q.cap]);
-                        m.ax = 0.0; m.ay = -P.g;
+                        mol_begin(m, P.g);
+                        m.t = t;
                         e = P.first_lens;
-                        step = 0;
-                        tb = table_of(P, P.el[e], smem_tab);
-                        lc = lens_consts(P.el[e], m);
+                        const DevElement &E = P.el[e];
+                        step = 0; n_steps = E.n_steps; bore_T = E.p[0];
+                        tb = table_of(E, smem_tab);
+                        lc = lens_consts(E, m);
                         have = true;
                     }
                 }
@@ -231,22 +238,25 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
             if (__ballot_sync(0xffffffffu, have) == 0) break;
         }
 
-        // ---- advance every busy lane by one RK step or one aperture ----
+        // ---- advance every busy lane: up to LENS_BURST RK steps, or one aperture ----
         int fate = -1;
         if (have) {
             CountRows rec;
             if (step >= 0) {
-                const DevElement &E = P.el[e];
-                int oob = 0;
-                lens_step(tb, lc, m, P.g, oob);
-                oob_total += oob;
-                ++steps_total;
-                ++step;
-                if (outside_radius(m, E.p[0])) fate = E.fate2;          // "Inside lens"
-                else if (step >= E.n_steps) {
-                    lens_exit(E, m, P.g, rec);
-                    step = -1;
-                    ++e;
+#pragma unroll 1
+                for (int b = 0; b < LENS_BURST; ++b) {
+                    int oob = 0;
+                    lens_step(tb, lc, r6, m, P.g, oob, reference_math);
+                    oob_total += oob;
+                    ++steps_total;
+                    ++step;
+                    if (outside_radius(m, bore_T)) { fate = P.el[e].fate2; break; }   // "Inside lens"
+                    if (step >= n_steps) {
+                        lens_exit(P.el[e], m, P.g, rec);
+                        step = -1;
+                        ++e;
+                        break;
+                    }
                 }
             } else if (e >= P.n_el) {
                 fate = P.fate_detected;
@@ -256,8 +266,8 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
                     to_plane(m, E.z0, P.g, rec);
                     if (outside_radius(m, E.p[0])) fate = E.fate;       // "Lens entrance"
                     else {
-                        step = 0;
-                        tb = table_of(P, E, smem_tab);
+                        step = 0; n_steps = E.n_steps; bore_T = E.p[0];
+                        tb = table_of(E, smem_tab);
                         lc = lens_consts(E, m);
                         if (E.n_steps <= 0) { lens_exit(E, m, P.g, rec); step = -1; ++e; }
                     }
@@ -287,8 +297,8 @@ trajectory_kernel(const __grid_constant__ Params P, int64_t n, const double *__r
                   double *__restrict__ rows, int max_rows, int32_t *__restrict__ n_rows,
                   uint8_t *__restrict__ fate_out)
 {
-    extern __shared__ double smem_tab[];
-    for (int i = threadIdx.x; i < 3 * P.tab_total; i += blockDim.x) smem_tab[i] = P.tab[i];
+    extern __shared__ double4 smem_tab[];
+    for (int i = threadIdx.x; i < P.tab_total; i += blockDim.x) smem_tab[i] = P.tab[i];
     __syncthreads();
 
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -297,12 +307,11 @@ trajectory_kernel(const __grid_constant__ Params P, int64_t n, const double *__r
     Mol m;
     m.x = state[0 * state_ld + col]; m.y = state[1 * state_ld + col]; m.z = state[2 * state_ld + col];
     m.vx = state[3 * state_ld + col]; m.vy = state[4 * state_ld + col]; m.vz = state[5 * state_ld + col];
+    mol_begin(m, P.g);
     if (n_comp >= 10) {
         // resume from an arbitrary row (BeamlineElement.propagate_through on a live Molecule)
         m.ax = state[6 * state_ld + col]; m.ay = state[7 * state_ld + col];
         m.t = state[9 * state_ld + col];
-    } else {
-        m.ax = 0.0; m.ay = -P.g; m.t = 0.0;
     }
     WriteRows rec;
     rec.base = rows + (size_t)j * max_rows * CMT_ROW_DOUBLES;
@@ -332,6 +341,64 @@ draw_kernel(const __grid_constant__ cmt_source_t S, uint64_t seed, int64_t first
         draw(S, seed, (uint64_t)(index ? index[j] : first_index + j), m);
         ic[0 * ld + j] = m.x; ic[1 * ld + j] = m.y; ic[2 * ld + j] = m.z;
         ic[3 * ld + j] = m.vx; ic[4 * ld + j] = m.vy; ic[5 * ld + j] = m.vz;
+    }
+}
+
+// Self-test of the shared-reciprocal division and the inline square root against
+// the compiler's own __ddiv_rn / __dsqrt_rn on pseudo-random operands.
+// out[0] = quotients that took the short sequence, out[1] = of those, bit mismatches,
+// out[2] = square roots that took the short sequence, out[3] = of those, bit mismatches,
+// out[4] = mismatches of dvd_cached (short sequence or fallback) against __ddiv_rn.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t &s)
+{
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ double random_double(uint64_t &s, int exp_lo, int exp_hi, bool allow_neg)
+{
+    const uint64_t w = splitmix64(s);
+    const uint64_t mant = w & 0x000FFFFFFFFFFFFFull;
+    const int e = exp_lo + (int)((w >> 52) % (uint64_t)(exp_hi - exp_lo + 1));
+    const uint64_t sign = allow_neg ? (w >> 63) << 63 : 0ull;
+    return __longlong_as_double((long long)(sign | ((uint64_t)(e + 1023) << 52) | mant));
+}
+
+__global__ void __launch_bounds__(256) selftest_kernel(int64_t n, uint64_t seed, int mode, unsigned long long *out)
+{
+    unsigned long long c[5] = {0, 0, 0, 0, 0};
+    const double r6 = rcp_refined(6.0);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(i + 1));
+        double a, b, sq;
+        if (mode == 0) {            // magnitudes of the lens integrator
+            a = random_double(s, -40, 12, true);
+            b = random_double(s, -20, -4, false);
+            sq = random_double(s, -40, -8, false);
+        } else if (mode == 1) {     // division by six
+            a = random_double(s, -60, 20, true);
+            b = 6.0;
+            sq = random_double(s, -200, 200, false);
+        } else {                    // everything, including the fallback ranges
+            a = random_double(s, -1022, 1023, true);
+            b = random_double(s, -1022, 1023, true);
+            sq = random_double(s, -1022, 1023, false);
+        }
+        const double want = __ddiv_rn(a, b);
+        bool ok = true;
+        const double y = (mode == 1) ? r6 : rcp_refined(b);
+        const double q = div_rcp(a, b, y, ok);
+        if (ok) { ++c[0]; if (__double_as_longlong(q) != __double_as_longlong(want)) ++c[1]; }
+        if (__double_as_longlong(dvd_cached(a, b, y)) != __double_as_longlong(want)) ++c[4];
+        bool ok2 = true;
+        const double r = sqrt_fast(sq, ok2);
+        if (ok2) { ++c[2]; if (__double_as_longlong(r) != __double_as_longlong(__dsqrt_rn(sq))) ++c[3]; }
+    }
+    for (int k = 0; k < 5; ++k) {
+        const unsigned long long v = c[k];
+        if (v) atomicAdd(out + k, v);
     }
 }
 

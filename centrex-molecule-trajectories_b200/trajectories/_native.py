@@ -83,6 +83,8 @@ _SIGNATURES = {
     "cmt_timing_enable": (C.c_int, [C.c_int]),
     "cmt_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "cmt_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "cmt_selftest": (C.c_int, [C.c_int, C.c_int64, C.c_uint64, C.c_int, C.POINTER(C.c_int64)]),
+    "cmt_debug_flags": (C.c_int, [C.c_int]),
     "cmt_version": (C.c_int, []),
     "cmt_last_error": (C.c_char_p, []),
 }

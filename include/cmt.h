@@ -194,6 +194,19 @@ int cmt_timing_read(double ms[4], int64_t launches[4], int reset);
  * streams), in operations per second; used as roofline denominators. */
 int cmt_fp64_peak(int device, double *dfma_per_s, double *dadd_per_s);
 
+/* Arithmetic self-test on `device`: n pseudo-random operands compare the
+ * shared-reciprocal division and the inline square root used by the kernels
+ * with __ddiv_rn / __dsqrt_rn bit for bit.  mode 0: lens-integrator magnitudes,
+ * 1: division by 6, 2: the whole binary64 range.  out[0] quotients that took the
+ * short sequence, out[1] mismatches among them, out[2]/out[3] the same for
+ * square roots, out[4] mismatches of the division with fallback. */
+int cmt_selftest(int device, int64_t n, uint64_t seed, int mode, int64_t out[5]);
+
+/* Debug switch read by cmt_beamline_create: bit 0 forces the plain-intrinsic
+ * arithmetic (no shared reciprocals) so both variants can be compared.
+ * Returns the previous value; a negative argument only queries. */
+int cmt_debug_flags(int flags);
+
 int cmt_version(void);
 const char *cmt_last_error(void);
 

@@ -295,3 +295,50 @@ def test_plugin_single_molecule(torch_cuda, golden_dir):
         m2.trajectory.drop_nans()
         got2 = np.concatenate([m2.trajectory.x, m2.trajectory.v, m2.trajectory.a, m2.trajectory.t[:, None]], axis=1)
         np.testing.assert_array_equal(got2, got)
+
+
+def test_arithmetic_selftest(torch_cuda, cuda_lib):
+    """The shared-reciprocal division and inline sqrt equal __ddiv_rn / __dsqrt_rn bit for bit."""
+    import ctypes as C
+
+    for mode, n in ((0, 200_000_000), (1, 200_000_000), (2, 400_000_000)):
+        out = (C.c_int64 * 5)()
+        assert cuda_lib.cmt_selftest(0, n, 0xC0FFEE + mode, mode, out) == 0, cuda_lib.cmt_last_error()
+        took_div, bad_div, took_sqrt, bad_sqrt, bad_cached = list(out)
+        assert bad_div == 0 and bad_sqrt == 0 and bad_cached == 0, (mode, list(out))
+        if mode < 2:
+            assert took_div == n and took_sqrt == n        # the short sequences cover the working range
+        else:
+            assert 0.5 * n < took_div < n and took_sqrt > 0.9 * n   # extremes fall back
+
+
+def test_fast_math_equals_reference_math(torch_cuda, cuda_lib):
+    """Kernels with shared reciprocals / FMA-carried power-of-two scalings give the same
+    bits as the same kernels forced onto the plain-intrinsic path."""
+    from trajectories import _engine as eng
+
+    torch = torch_cuda
+    bl = lens_beamline(lens_table())
+    ic = torch.from_numpy(standard_ics(300000, 77, 3.0)).cuda()
+    flat = eng.flatten(bl.elements)
+    outs = []
+    for flags in (0, 1):
+        old = cuda_lib.cmt_debug_flags(flags)
+        try:
+            prop = eng.Propagator(flat, 0)
+            prop.dev = eng.DeviceBeamline(flat, 0)          # bypass the handle cache: flags are read at creation
+            prop.reset()
+            res = prop.propagate_ic(ic, want_fate=True, want_final=True)
+            rows, n_rows, fate = prop.trajectories(ic[:, :2000].contiguous())
+            torch.cuda.synchronize()
+            outs.append((res.fate.cpu().numpy(), res.final.cpu().numpy(), res.work.cpu().numpy(), rows, n_rows))
+        finally:
+            cuda_lib.cmt_debug_flags(old)
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1].view(np.int64), outs[1][1].view(np.int64))
+    np.testing.assert_array_equal(outs[0][2], outs[1][2])
+    np.testing.assert_array_equal(outs[0][4], outs[1][4])
+    for k in range(2000):
+        n = outs[0][4][k]
+        np.testing.assert_array_equal(outs[0][3][k, :n].view(np.int64), outs[1][3][k, :n].view(np.int64))
+    assert outs[0][2][1] > 50_000_000                      # tens of millions of RK steps compared
