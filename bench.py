@@ -289,7 +289,7 @@ def run_ours(args):
     ic_host.copy_(ic)
     fate_host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     cnt_host = np.zeros(len(prop.flat.fate_names), dtype=np.int64)
-    work_host = np.zeros(4, dtype=np.int64)
+    work_host = np.zeros(8, dtype=np.int64)
     torch.cuda.synchronize()
 
     def e2e_step():
@@ -355,7 +355,8 @@ def run_ours(args):
             "clocks": clocks,
             "counters": dict(zip(prop.flat.fate_names, counters.tolist())),
             "work_per_step": {"ballistic_rows": int(work[0]), "lens_rk_steps": int(work[1]),
-                              "table_out_of_range": int(work[2]), "lens_entries": int(work[3])},
+                              "table_out_of_range": int(work[2]), "lens_entries": int(work[3]),
+                              "rk_steps_on_reference_path": int(work[4])},
             "kernel_ms_per_step": {"walk": walk_ms, "lens": lens_ms},
         }
         print(json.dumps(line), flush=True)

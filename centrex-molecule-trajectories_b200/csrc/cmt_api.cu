@@ -57,7 +57,7 @@ struct cmt_beamline {
     int device;
     int max_rows;
     int n_sm;
-    double4 *d_tab;     // [tab_total]: (r_j, a_j, slope_j, r_{j+1})
+    double4 *d_tab;     // [tab_total]: (r_j, r_{j+1}, a_j, slope_j)
     size_t tab_bytes;   // dynamic shared memory the lens/trajectory kernels need
 };
 
@@ -184,15 +184,15 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
             for (int i = 0; i < tb.n; ++i) {
                 double4 &e = h[tab_off[t] + i];
                 e.x = tb.r[i];
-                e.y = tb.a[i];
-                e.z = 0.0;
-                e.w = std::numeric_limits<double>::infinity();
+                e.y = -std::numeric_limits<double>::infinity();
+                e.z = tb.a[i];
+                e.w = 0.0;
                 if (i + 1 < tb.n) {
                     // np.interp: slope = (fp[j+1]-fp[j]) / (xp[j+1]-xp[j]); same IEEE ops here
                     volatile double num = tb.a[i + 1] - tb.a[i];
                     volatile double den = tb.r[i + 1] - tb.r[i];
-                    e.z = num / den;
-                    e.w = tb.r[i + 1];
+                    e.y = tb.r[i + 1];
+                    e.w = num / den;
                 }
             }
         }
@@ -442,7 +442,7 @@ struct HostPipe {
     double *d_final[2] = {nullptr, nullptr};
     void *d_ws[2] = {nullptr, nullptr};
     size_t ws_bytes = 0;
-    int64_t *d_cnt = nullptr;   // [CMT_MAX_FATES + 4]
+    int64_t *d_cnt = nullptr;   // [CMT_MAX_FATES + CMT_WORK_SLOTS]
 
     void release()
     {
@@ -483,17 +483,17 @@ int pipe_prepare(HostPipe &p, const cmt_beamline_t *bl, int64_t chunk, bool want
         if (keep_fate) CUDA_TRY(cudaMalloc(&p.d_fate[k], (size_t)chunk));
         if (keep_final) CUDA_TRY(cudaMalloc(&p.d_final[k], (size_t)10 * chunk * sizeof(double)));
     }
-    CUDA_TRY(cudaMalloc(&p.d_cnt, (CMT_MAX_FATES + 4) * sizeof(int64_t)));
+    CUDA_TRY(cudaMalloc(&p.d_cnt, (CMT_MAX_FATES + CMT_WORK_SLOTS) * sizeof(int64_t)));
     return CMT_OK;
 }
 
 int pipe_collect(HostPipe &p, const cmt_beamline_t *bl, int64_t *counters_host, int64_t *work_host)
 {
     for (int k = 0; k < 2; ++k) CUDA_TRY(cudaStreamSynchronize(p.st[k]));
-    int64_t h[CMT_MAX_FATES + 4];
+    int64_t h[CMT_MAX_FATES + CMT_WORK_SLOTS];
     CUDA_TRY(cudaMemcpy(h, p.d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
     for (int f = 0; f < bl->P.n_fates; ++f) counters_host[f] += h[f];
-    if (work_host) for (int k = 0; k < 4; ++k) work_host[k] += h[CMT_MAX_FATES + k];
+    if (work_host) for (int k = 0; k < CMT_WORK_SLOTS; ++k) work_host[k] += h[CMT_MAX_FATES + k];
     return CMT_OK;
 }
 
@@ -512,7 +512,7 @@ extern "C" int cmt_run_host_ic(const cmt_beamline_t *bl, int64_t n, const double
     const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 21);
     int rc = pipe_prepare(p, bl, chunk, true, fate_host != nullptr, final_host != nullptr);
     if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(p.d_cnt, 0, (CMT_MAX_FATES + 4) * sizeof(int64_t), p.st[0]));
+    CUDA_TRY(cudaMemsetAsync(p.d_cnt, 0, (CMT_MAX_FATES + CMT_WORK_SLOTS) * sizeof(int64_t), p.st[0]));
     CUDA_TRY(cudaStreamSynchronize(p.st[0]));
 
     const size_t dpitch = (size_t)p.chunk * sizeof(double), hpitch = (size_t)n * sizeof(double);
@@ -552,7 +552,7 @@ extern "C" int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t 
     const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 24);
     int rc = pipe_prepare(p, bl, chunk, false, false, false);
     if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(p.d_cnt, 0, (CMT_MAX_FATES + 4) * sizeof(int64_t), p.st[0]));
+    CUDA_TRY(cudaMemsetAsync(p.d_cnt, 0, (CMT_MAX_FATES + CMT_WORK_SLOTS) * sizeof(int64_t), p.st[0]));
     CUDA_TRY(cudaStreamSynchronize(p.st[0]));
     const int64_t n_chunks = (n + chunk - 1) / chunk;
     for (int64_t ci = 0; ci < n_chunks; ++ci) {

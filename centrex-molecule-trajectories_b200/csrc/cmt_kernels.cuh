@@ -38,7 +38,7 @@ struct Queue {
 
 struct BlockAcc {
     unsigned int hist[CMT_MAX_FATES];
-    unsigned long long work[4];
+    unsigned long long work[CMT_WORK_SLOTS];
 };
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
@@ -58,7 +58,7 @@ __device__ __forceinline__ long long warp_append(bool pred, unsigned long long *
 __device__ __forceinline__ void block_acc_init(BlockAcc &acc)
 {
     for (int i = threadIdx.x; i < CMT_MAX_FATES; i += blockDim.x) acc.hist[i] = 0;
-    if (threadIdx.x < 4) acc.work[threadIdx.x] = 0;
+    if (threadIdx.x < CMT_WORK_SLOTS) acc.work[threadIdx.x] = 0;
     __syncthreads();
 }
 
@@ -67,7 +67,7 @@ __device__ __forceinline__ void block_acc_flush(BlockAcc &acc, const Params &P, 
     __syncthreads();
     for (int i = threadIdx.x; i < P.n_fates; i += blockDim.x)
         if (acc.hist[i]) atomicAdd((unsigned long long *)O.counters + i, (unsigned long long)acc.hist[i]);
-    if (O.work && threadIdx.x < 4 && acc.work[threadIdx.x])
+    if (O.work && threadIdx.x < CMT_WORK_SLOTS && acc.work[threadIdx.x])
         atomicAdd((unsigned long long *)O.work + threadIdx.x, acc.work[threadIdx.x]);
 }
 
@@ -184,13 +184,15 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
 {
     extern __shared__ double4 smem_tab[];
     __shared__ BlockAcc acc;
+    const unsigned long long count = min(*Q.count, (unsigned long long)Q.cap);
+    // When the queue cannot fill every lane, only the first ceil(count/128) CTAs take part:
+    // consecutive CTAs land on different SMs, so the survivors spread evenly over the chip.
+    if ((unsigned long long)blockIdx.x * LENS_THREADS >= count) return;
     for (int i = threadIdx.x; i < P.tab_total; i += blockDim.x) smem_tab[i] = P.tab[i];
     block_acc_init(acc);
-
-    const unsigned long long count = min(*Q.count, (unsigned long long)Q.cap);
     const bool reference_math = (P.flags & CMT_FLAG_REFERENCE_MATH) != 0;
     const double r6 = rcp_refined(6.0);
-    unsigned rows_total = 0, steps_total = 0, oob_total = 0;
+    unsigned rows_total = 0, steps_total = 0, oob_total = 0, ref_total = 0;
 
     Mol m;
     m.x = m.y = m.z = m.vx = m.vy = m.t = m.ax = m.ay = 0.0; m.vz = 1.0; m.rvz = 1.0;
@@ -247,7 +249,8 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
                 for (int b = 0; b < LENS_BURST; ++b) {
                     int oob = 0;
                     lens_step(tb, lc, r6, m, P.g, oob, reference_math);
-                    oob_total += oob;
+                    oob_total += oob & 0xffff;
+                    ref_total += oob >> 16;
                     ++steps_total;
                     ++step;
                     if (outside_radius(m, bore_T)) { fate = P.el[e].fate2; break; }   // "Inside lens"
@@ -285,6 +288,7 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
     warp_add_work(acc, 0, rows_total);
     warp_add_work(acc, 1, steps_total);
     warp_add_work(acc, 2, oob_total);
+    warp_add_work(acc, 4, ref_total);
     block_acc_flush(acc, P, O);
 }
 
@@ -392,6 +396,12 @@ __global__ void __launch_bounds__(256) selftest_kernel(int64_t n, uint64_t seed,
         const double q = div_rcp(a, b, y, ok);
         if (ok) { ++c[0]; if (__double_as_longlong(q) != __double_as_longlong(want)) ++c[1]; }
         if (__double_as_longlong(dvd_cached(a, b, y)) != __double_as_longlong(want)) ++c[4];
+        {   // the mid-window variant as mol_begin/time_to use it
+            const float f = fabsf(__int_as_float(__double2hiint(b)));
+            const bool mid = (f >= __int_as_float(0x26F00000)) && (f <= __int_as_float(0x58F00000));
+            const double ym = mid ? y : __longlong_as_double(0x7ff8000000000000ll);
+            if (__double_as_longlong(dvd_cached_mid(a, b, ym)) != __double_as_longlong(want)) ++c[4];
+        }
         bool ok2 = true;
         const double r = sqrt_fast(sq, ok2);
         if (ok2) { ++c[2]; if (__double_as_longlong(r) != __double_as_longlong(__dsqrt_rn(sq))) ++c[3]; }

@@ -225,7 +225,7 @@ class Propagator:
         torch = _torch()
         self.tdev = torch.device("cuda", self.device)
         self.counters = torch.zeros(len(self.flat.fate_names), dtype=torch.int64, device=self.tdev)
-        self.work = torch.zeros(4, dtype=torch.int64, device=self.tdev)
+        self.work = torch.zeros(8, dtype=torch.int64, device=self.tdev)
         self.saved_count = torch.zeros(1, dtype=torch.int64, device=self.tdev)
 
     def reset(self):

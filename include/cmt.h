@@ -41,6 +41,7 @@ extern "C" {
 #define CMT_MAX_ELEMENTS 40      /* element table lives in kernel-parameter constant memory */
 #define CMT_MAX_FATES 64         /* fates are stored as uint8 and selected by a 64-bit mask */
 #define CMT_MAX_TABLES 8
+#define CMT_WORK_SLOTS 8         /* length of the work-counter array */
 #define CMT_ROW_DOUBLES 10       /* x,y,z,vx,vy,vz,ax,ay,az,t: one Trajectory row (molecule.py:133-144) */
 
 /* error codes */
@@ -105,7 +106,8 @@ typedef struct cmt_outputs {
     double *final_state;    /* [10][final_ld] SoA last trajectory row per molecule (x,y,z,vx,vy,vz,ax,ay,az,t), or NULL */
     int64_t final_ld;       /* leading dimension of final_state (>= n) */
     int64_t *counters;      /* [n_fates] per-fate counts, ACCUMULATED (Counter, trajectory_simulator.py:106-124); required */
-    int64_t *work;          /* [4] accumulated: ballistic rows, lens RK steps, table out-of-range evaluations, lens entries; or NULL */
+    int64_t *work;          /* [CMT_WORK_SLOTS] accumulated: ballistic rows, lens RK steps, table out-of-range
+                             * evaluations, lens entries, RK steps that took the plain-intrinsic path, 3 reserved; or NULL */
     int64_t *saved_index;   /* [saved_capacity] global indices of molecules whose fate is in save_mask (unordered), or NULL */
     int64_t *saved_count;   /* [1] accumulated cursor into saved_index (may exceed capacity: then the list is truncated) */
     int64_t saved_capacity;
@@ -169,7 +171,7 @@ int cmt_trajectories(const cmt_beamline_t *bl, int64_t n, const double *state, i
 /* ---- host-buffer convenience (what a non-CUDA host language binds) ------ */
 
 /* ic_host [6][n] (SoA, row-major), fate_host [n] or NULL, final_host [10][n]
- * or NULL, counters_host [n_fates] (accumulated), work_host [4] or NULL
+ * or NULL, counters_host [n_fates] (accumulated), work_host [CMT_WORK_SLOTS] or NULL
  * (accumulated).  Stages through pinned buffers in chunks on two streams so
  * PCIe copies overlap the kernels; returns after everything has landed. */
 int cmt_run_host_ic(const cmt_beamline_t *bl, int64_t n, const double *ic_host,

@@ -106,6 +106,7 @@ def test_oracle_lens_beamline(torch_cuda, n, seed, sigma):
     np.testing.assert_array_equal(got["fate"], want["fate"])
     np.testing.assert_array_equal(got["counters"], want["counters"])
     np.testing.assert_array_equal(got["work"][:3], want["work"])
+    assert got["work"][4] <= 1e-4 * max(got["work"][1], 1) + 2     # the straight-line RK step almost never falls back
     assert relerr(got["fin"], want["fin"]) < TIGHT
     same = (got["fin"].view(np.int64) == want["fin"].view(np.int64)).mean()
     assert same > 0.995          # almost every value is bit-identical (pow() vs exact square)
@@ -201,7 +202,7 @@ def test_host_buffer_entry(torch_cuda, cuda_lib):
     fate = np.empty(n, dtype=np.uint8)
     fin = np.empty((10, n))
     counters = np.zeros(len(prop.flat.fate_names), dtype=np.int64)
-    work = np.zeros(4, dtype=np.int64)
+    work = np.zeros(8, dtype=np.int64)
     rc = cuda_lib.cmt_run_host_ic(prop.dev.handle, n, ic.ctypes.data, fate.ctypes.data, fin.ctypes.data,
                                   counters.ctypes.data, work.ctypes.data)
     assert rc == 0, cuda_lib.cmt_last_error()
@@ -336,7 +337,8 @@ def test_fast_math_equals_reference_math(torch_cuda, cuda_lib):
             cuda_lib.cmt_debug_flags(old)
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     np.testing.assert_array_equal(outs[0][1].view(np.int64), outs[1][1].view(np.int64))
-    np.testing.assert_array_equal(outs[0][2], outs[1][2])
+    np.testing.assert_array_equal(outs[0][2][:4], outs[1][2][:4])
+    assert outs[0][2][4] == 0 and outs[1][2][4] == outs[1][2][1]     # RK steps on the plain-intrinsic path: none / all
     np.testing.assert_array_equal(outs[0][4], outs[1][4])
     for k in range(2000):
         n = outs[0][4][k]
