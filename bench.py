@@ -215,27 +215,59 @@ def run_ours(args):
     ic = prop.draw(source, seed, first, n)         # synthetic CeNTREX-shaped ICs, resident in HBM
     torch.cuda.synchronize()
 
-    def step():
-        res = prop.propagate_ic(ic, first_index=first, want_fate=True)
-        if world > 1:
-            dist.all_reduce(prop.counters)         # the Counter merge (tiny, NCCL over NVLink)
-        return res
+    def step(slot=None):
+        return prop.propagate_ic(ic, first_index=first, want_fate=True, slot=slot)
 
-    # ---- value: device-resident inputs ----
-    for _ in range(max(args.warmup, 3)):
+    def merge_counter():
+        prop.join()
+        if world > 1:
+            dist.all_reduce(prop.counters)         # the Counter merge (tiny, NCCL over NVLink), once per run
+            dist.all_reduce(prop.work)
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         prop.reset()
-        step()
+        res = step()
+    torch.cuda.synchronize()
+    counters1 = res.counters.cpu().numpy().copy()  # one step of this rank
+    work1 = res.work.cpu().numpy().copy()
+    work = work1
+
+    # ---- pass A: K steps back to back on one stream, every kernel timed with CUDA events ----
     barrier()
     lib.cmt_timing_enable(1)
     lib.cmt_timing_read(None, None, 1)
+    prop.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step()
+    merge_counter()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms_seq = max_over_ranks(e0.elapsed_time(e1))
+    ms_k = (C.c_double * 4)()
+    n_k = (C.c_int64 * 4)()
+    lib.cmt_timing_read(ms_k, n_k, 1)
+    lib.cmt_timing_enable(0)
+    launches = int(n_k[0] + n_k[1])
+
+    # ---- pass B (the headline value): the same K steps, consecutive steps on alternating streams so
+    # that the lens integrator of one batch overlaps the walk kernel of the next ----
+    slots = [None] * args.steps if args.no_overlap else [k % prop.n_slots for k in range(args.steps)]
+    for k in range(warm):
+        step(slots[k % len(slots)])
+    prop.join()
+    barrier()
     sampler = ClockSampler(local)
     prop.reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     e0.record()
-    for _ in range(args.steps):
-        prop.reset()
-        res = step()
+    for k in range(args.steps):
+        res = step(slots[k])
+    merge_counter()
     e1.record()
     while not e1.query():
         time.sleep(0.002)
@@ -243,13 +275,16 @@ def run_ours(args):
     clocks = sampler.stop()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    ms_k = (C.c_double * 4)()
-    n_k = (C.c_int64 * 4)()
-    lib.cmt_timing_read(ms_k, n_k, 1)
-    lib.cmt_timing_enable(0)
     counters = res.counters.cpu().numpy()
-    work = res.work.cpu().numpy()                  # of the last step (reset each step)
+    total_expected = counters1 * args.steps
+    if world > 1:
+        t = torch.from_numpy(total_expected).cuda()
+        dist.all_reduce(t)
+        total_expected = t.cpu().numpy()
+    assert (counters == total_expected).all(), "Counter of the timed run differs from K x one step"
+    counters = counters1
     value = world * n * args.steps / (ms * 1e-3)
+    value_seq = world * n * args.steps / (ms_seq * 1e-3)
 
     # ---- roofline ----
     dfma, dadd = C.c_double(), C.c_double()
@@ -272,7 +307,8 @@ def run_ours(args):
         "unit": "TFLOP/s", "frac": (lens_tflops / fp64_peak_tflops) if lens_tflops else None, "traffic": None,
         "peak_source": "measured live: cmt_fp64_peak DFMA stream (no FP64 figure in MEASURED_PEAKS.json)",
         "algorithmic_flop_per_launch": flop_lens, "avg_launch_ms": lens_ms,
-        "share_of_step": lens_ms / (ms / args.steps) if ms > 0 else None,
+        "share_of_step": lens_ms / (ms_seq / args.steps) if ms_seq > 0 else None,
+        "timed_in": "pass A: the same K steps back to back on one stream (kernels not overlapped), CUDA events per launch",
         "dadd_peak_tops": dadd.value / 1e12,
     }
     walk_gbs = BYTES_PER_MOLECULE * n / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else None
@@ -280,7 +316,7 @@ def run_ours(args):
         "kernel": "walk_kernel<ic>", "bound": "hbm", "achieved": walk_gbs, "peak": hbm_peak, "unit": "GB/s",
         "frac": (walk_gbs / hbm_peak) if walk_gbs else None, "traffic": None, "peak_source": hbm_src,
         "algorithmic_bytes_per_launch": BYTES_PER_MOLECULE * n, "avg_launch_ms": walk_ms,
-        "share_of_step": walk_ms / (ms / args.steps) if ms > 0 else None,
+        "share_of_step": walk_ms / (ms_seq / args.steps) if ms_seq > 0 else None,
         "algorithmic_flop_per_launch": flop_rows,
     }
 
@@ -349,7 +385,9 @@ def run_ours(args):
             "e2e_philox": {"value": philox_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * (len(cnt_host) + 4),
                            "path": "cmt_run_host_philox (run_simulation default): Philox4x32-10 source on device, Counter D2H",
                            "counters_match_device_run": philox_same},
-            "gpu_launches": int(n_k[0] + n_k[1]),
+            "gpu_launches": launches,
+            "value_one_stream": value_seq, "ms_per_step_one_stream": ms_seq / args.steps,
+            "overlap": "none" if args.no_overlap else f"{prop.n_slots} streams: consecutive steps alternate streams (independent batches)",
             "roofline": roofline, "roofline_walk": roofline_walk,
             "cpu_baseline": cpu,
             "clocks": clocks,
@@ -373,6 +411,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--molecules", type=float, default=1e7, help="molecules per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true", help="issue every step on one stream")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

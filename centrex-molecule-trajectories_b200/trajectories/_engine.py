@@ -215,31 +215,76 @@ class PropagateResult:
 
 
 class Propagator:
-    """Reusable launch context: beamline handle + scratch buffers on one device."""
+    """Reusable launch context: beamline handle + scratch buffers on one device.
 
-    def __init__(self, elements_or_flat, device=None):
+    Launches normally go to the current CUDA stream.  With `slot=k` a launch goes to one of
+    `n_slots` private streams (each with its own workspace), so consecutive chunks overlap:
+    the lens integrator of chunk i, which cannot fill the chip on its own at 1e7 molecules,
+    runs beside the walk kernel of chunk i+1.  `join()` makes the current stream wait for them.
+    """
+
+    def __init__(self, elements_or_flat, device=None, n_slots: int = 2):
         self.flat = elements_or_flat if isinstance(elements_or_flat, FlatBeamline) else flatten(elements_or_flat)
         self.device = resolve_device(device)
         self.dev = device_beamline(self.flat, self.device)
-        self._ws = None
         torch = _torch()
         self.tdev = torch.device("cuda", self.device)
         self.counters = torch.zeros(len(self.flat.fate_names), dtype=torch.int64, device=self.tdev)
         self.work = torch.zeros(8, dtype=torch.int64, device=self.tdev)
-        self.saved_count = torch.zeros(1, dtype=torch.int64, device=self.tdev)
+        self.n_slots = int(n_slots)
+        self._ws = [None] * (self.n_slots + 1)           # last entry: launches on the current stream
+        self._saved_count = [torch.zeros(1, dtype=torch.int64, device=self.tdev) for _ in range(self.n_slots + 1)]
+        self._streams = None
 
     def reset(self):
+        self.join()
         self.counters.zero_()
         self.work.zero_()
 
-    def _workspace(self, n: int):
+    # -- streams ---------------------------------------------------------------
+    def _slot_stream(self, slot):
+        torch = _torch()
+        if self._streams is None:
+            with torch.cuda.device(self.device):
+                self._streams = [torch.cuda.Stream(device=self.tdev) for _ in range(self.n_slots)]
+        return self._streams[slot % self.n_slots]
+
+    def join(self):
+        """Make the current stream wait for every slot stream."""
+        if self._streams is not None:
+            cur = _torch().cuda.current_stream(self.device)
+            for st in self._streams:
+                cur.wait_stream(st)
+
+    class _Launch:
+        def __init__(self, prop, slot):
+            self.prop, self.slot, self.ctx = prop, slot, None
+
+        def __enter__(self):
+            torch = _torch()
+            p = self.prop
+            if self.slot is None:
+                self.index = p.n_slots
+                self.ctx = torch.cuda.device(p.device)
+            else:
+                st = p._slot_stream(self.slot)
+                st.wait_stream(torch.cuda.current_stream(p.device))   # inputs produced on the caller's stream
+                self.index = self.slot % p.n_slots
+                self.ctx = torch.cuda.stream(st)
+            self.ctx.__enter__()
+            return self
+
+        def __exit__(self, *exc):
+            return self.ctx.__exit__(*exc)
+
+    def _workspace(self, n: int, index: int):
         torch = _torch()
         need = self.dev.workspace_bytes(n)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.tdev)
-        return self._ws
+        if self._ws[index] is None or self._ws[index].numel() < need:
+            self._ws[index] = torch.empty(need, dtype=torch.uint8, device=self.tdev)
+        return self._ws[index]
 
-    def _outputs(self, n, want_fate, want_final, save_mask, saved_buf):
+    def _outputs(self, n, want_fate, want_final, save_mask, saved_buf, index):
         torch = _torch()
         O = nat.Outputs()
         fate = final = None
@@ -252,49 +297,50 @@ class Propagator:
         O.counters = self.counters.data_ptr()
         O.work = self.work.data_ptr()
         if save_mask:
-            self.saved_count.zero_()
+            self._saved_count[index].zero_()
             O.saved_index = saved_buf.data_ptr()
-            O.saved_count = self.saved_count.data_ptr()
+            O.saved_count = self._saved_count[index].data_ptr()
             O.saved_capacity = saved_buf.numel()
             O.save_mask = save_mask
         return O, fate, final
 
-    def _finish_saved(self, save_mask, saved_buf):
+    def _finish_saved(self, save_mask, saved_buf, index):
         if not save_mask:
             return None
         torch = _torch()
-        k = int(self.saved_count.item())
+        k = int(self._saved_count[index].item())
         if k > saved_buf.numel():
             raise RuntimeError("saved-index buffer overflow")  # cannot happen: capacity == n
         return torch.sort(saved_buf[:k]).values
 
-    def propagate_ic(self, ic, first_index=0, want_fate=True, want_final=False, save_mask=0) -> PropagateResult:
+    def propagate_ic(self, ic, first_index=0, want_fate=True, want_final=False, save_mask=0,
+                     slot=None) -> PropagateResult:
         """ic: torch float64 [6, n] on this device (SoA x,y,z,vx,vy,vz)."""
         torch = _torch()
         assert ic.dtype == torch.float64 and ic.dim() == 2 and ic.shape[0] == 6 and ic.is_cuda
         assert ic.shape[1] == 0 or ic.stride(1) == 1
         n = ic.shape[1]
-        ws = self._workspace(n)
-        saved_buf = torch.empty(n, dtype=torch.int64, device=self.tdev) if save_mask else None
-        O, fate, final = self._outputs(n, want_fate, want_final, save_mask, saved_buf)
-        with torch.cuda.device(self.device):
+        with self._Launch(self, slot) as L:
+            ws = self._workspace(n, L.index)
+            saved_buf = torch.empty(n, dtype=torch.int64, device=self.tdev) if save_mask else None
+            O, fate, final = self._outputs(n, want_fate, want_final, save_mask, saved_buf, L.index)
             nat.check(nat.lib().cmt_propagate_ic(self.dev.handle, n, int(first_index), ic.data_ptr(), ic.stride(0),
                                                  C.byref(O), ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
-        return PropagateResult(self.counters, self.work, fate, final, self._finish_saved(save_mask, saved_buf),
-                               self.flat.fate_names)
+            saved = self._finish_saved(save_mask, saved_buf, L.index)
+        return PropagateResult(self.counters, self.work, fate, final, saved, self.flat.fate_names)
 
     def propagate_philox(self, source: nat.Source, seed: int, first_index: int, n: int, want_fate=False,
-                         want_final=False, save_mask=0) -> PropagateResult:
+                         want_final=False, save_mask=0, slot=None) -> PropagateResult:
         torch = _torch()
-        ws = self._workspace(n)
-        saved_buf = torch.empty(n, dtype=torch.int64, device=self.tdev) if save_mask else None
-        O, fate, final = self._outputs(n, want_fate, want_final, save_mask, saved_buf)
-        with torch.cuda.device(self.device):
+        with self._Launch(self, slot) as L:
+            ws = self._workspace(n, L.index)
+            saved_buf = torch.empty(n, dtype=torch.int64, device=self.tdev) if save_mask else None
+            O, fate, final = self._outputs(n, want_fate, want_final, save_mask, saved_buf, L.index)
             nat.check(nat.lib().cmt_propagate_philox(self.dev.handle, C.byref(source), int(seed) & (2**64 - 1),
                                                      int(first_index), int(n), C.byref(O), ws.data_ptr(),
                                                      ws.numel(), _stream_ptr(self.device)))
-        return PropagateResult(self.counters, self.work, fate, final, self._finish_saved(save_mask, saved_buf),
-                               self.flat.fate_names)
+            saved = self._finish_saved(save_mask, saved_buf, L.index)
+        return PropagateResult(self.counters, self.work, fate, final, saved, self.flat.fate_names)
 
     def draw(self, source: nat.Source, seed: int, first_index: int = 0, n: int = 0, index=None):
         """Materialise source samples as a device tensor [6, n]."""
