@@ -67,14 +67,15 @@ def cpu_rate(bl, vdist, xdist, target_s: float, seed: int = 1):
 
     src = oracle.make_source(vdist, xdist)
     flat = oracle.flatten(bl.elements)
-    threads = oracle.max_threads()
+    threads = oracle.host_cores()                 # all host cores (torchrun would pin OpenMP to 1)
     n = 200_000
+    oracle.run(flat, src, seed, 0, n, n_threads=threads)
     t0 = time.perf_counter()
-    oracle.run(flat, src, seed, 0, n)
+    oracle.run(flat, src, seed, 0, n, n_threads=threads)
     probe = time.perf_counter() - t0
     n = int(max(n, min(2e9, n * target_s / max(probe, 1e-3))))
     t0 = time.perf_counter()
-    res = oracle.run(flat, src, seed, 10_000_000_000, n)
+    res = oracle.run(flat, src, seed, 10_000_000_000, n, n_threads=threads)
     dt = time.perf_counter() - t0
     return dict(value=n / dt, n=n, seconds=dt, cores=threads, counters=res["counters"].tolist())
 
@@ -88,17 +89,18 @@ def run_reference(args):
     bl, vdist, xdist = build_workload()
     src = oracle.make_source(vdist, xdist)
     flat = oracle.flatten(bl.elements)
-    threads = oracle.max_threads()
+    threads = oracle.host_cores()                 # all host cores (torchrun would pin OpenMP to 1)
+    oracle.run(flat, src, 1, 0, 200_000, n_threads=threads)
     t0 = time.perf_counter()
-    oracle.run(flat, src, 1, 0, 200_000)
+    oracle.run(flat, src, 1, 0, 200_000, n_threads=threads)
     probe = time.perf_counter() - t0
     # each step a bounded sample: ~2.5 s of host work, so K+W steps end within a few minutes
-    per_step = int(max(200_000, 200_000 * 2.5 / max(probe, 1e-3)))
+    per_step = int(min(1e7, max(200_000, 200_000 * 2.5 / max(probe, 1e-3))))
     for w in range(args.warmup):
-        oracle.run(flat, src, 1, (w + 1) * per_step, per_step)
+        oracle.run(flat, src, 1, (w + 1) * per_step, per_step, n_threads=threads)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        oracle.run(flat, src, 1, (args.warmup + k + 1) * per_step, per_step)
+        oracle.run(flat, src, 1, (args.warmup + k + 1) * per_step, per_step, n_threads=threads)
     dt = time.perf_counter() - t0
     value = args.steps * per_step / dt
     sample = f"{per_step} molecules per step (bounded sample of the 1e7-molecule step), Philox source + propagation + Counter"

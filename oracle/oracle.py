@@ -216,3 +216,12 @@ def run(elements, source: np.ndarray, seed: int, first: int, n: int, n_threads: 
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+def host_cores() -> int:
+    """Cores this process may run on.  torchrun exports OMP_NUM_THREADS=1, so callers that
+    want every core pass this explicitly as n_threads."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1

@@ -1,0 +1,85 @@
+"""A tiny in-memory stand-in for h5py (absent from the image) that records groups,
+attributes and datasets, so the HDF5 *layout* written by the package can be checked
+against the reference's without libhdf5."""
+from __future__ import annotations
+
+import numpy as np
+
+STORE = {}   # path of the file -> root Group
+
+
+class Dataset:
+    def __init__(self, data):
+        self.data = np.array(data)
+        self.shape, self.dtype = self.data.shape, self.data.dtype
+
+    def __getitem__(self, key):
+        return self.data[key]
+
+
+class Group:
+    def __init__(self):
+        self.attrs = {}
+        self.children = {}
+
+    def _walk(self, path, create=False):
+        node = self
+        for part in [p for p in path.split("/") if p]:
+            if part not in node.children:
+                if not create:
+                    raise KeyError(path)
+                node.children[part] = Group()
+            node = node.children[part]
+        return node
+
+    def create_group(self, path):
+        parts = [p for p in path.split("/") if p]
+        parent = self._walk("/".join(parts[:-1]), create=True)
+        if parts[-1] in parent.children:
+            raise ValueError("Unable to create group (name already exists)")
+        parent.children[parts[-1]] = Group()
+        return parent.children[parts[-1]]
+
+    def create_dataset(self, name, data=None):
+        parts = [p for p in name.split("/") if p]
+        parent = self._walk("/".join(parts[:-1]), create=True)
+        parent.children[parts[-1]] = Dataset(data)
+        return parent.children[parts[-1]]
+
+    def __getitem__(self, path):
+        return self._walk(path)
+
+    def __delitem__(self, path):
+        parts = [p for p in path.split("/") if p]
+        del self._walk("/".join(parts[:-1])).children[parts[-1]]
+
+    def __contains__(self, path):
+        try:
+            self._walk(path)
+            return True
+        except KeyError:
+            return False
+
+    def keys(self):
+        return self.children.keys()
+
+
+class File(Group):
+    def __new__(cls, path, mode="r"):
+        key = str(path)
+        if key not in STORE:
+            if mode == "r":
+                raise OSError(f"no such file {key}")
+            root = super().__new__(cls)
+            Group.__init__(root)
+            STORE[key] = root
+        return STORE[key]
+
+    def __init__(self, path, mode="r"):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
