@@ -357,15 +357,16 @@ class Propagator:
     def trajectories(self, state, select=None, select_base=0):
         """Full rows for the molecules in `state` ([6|10, m] device tensor), optionally
         gathered through `select` (global indices, device int64).  Returns host arrays
-        (rows [k, max_rows, 10] NaN-free up to n_rows[k], n_rows [k], fate [k])."""
+        (rows [k, max_rows, 10] valid up to n_rows[k], n_rows [k], fate [k]).  The rows land
+        in pinned host memory straight from the device (no pageable staging copy)."""
         torch = _torch()
         n_comp = state.shape[0]
         k_total = select.numel() if select is not None else state.shape[1]
         max_rows = self.dev.max_rows
         per = max(1, min(k_total, ROW_BUDGET_BYTES // (max_rows * nat.CMT_ROW_DOUBLES * 8)))
-        rows_out = np.empty((k_total, max_rows, nat.CMT_ROW_DOUBLES), dtype=np.float64)
-        n_rows_out = np.empty(k_total, dtype=np.int32)
-        fate_out = np.empty(k_total, dtype=np.uint8)
+        rows_host = torch.empty((k_total, max_rows, nat.CMT_ROW_DOUBLES), dtype=torch.float64, pin_memory=True)
+        n_rows_host = torch.empty(k_total, dtype=torch.int32, pin_memory=True)
+        fate_host = torch.empty(k_total, dtype=torch.uint8, pin_memory=True)
         for lo in range(0, k_total, per):
             hi = min(k_total, lo + per)
             m = hi - lo
@@ -380,10 +381,11 @@ class Propagator:
                 nat.check(nat.lib().cmt_trajectories(self.dev.handle, m, st_ptr, n_comp, state.stride(0), sel_ptr,
                                                      int(select_base), rows.data_ptr(), max_rows,
                                                      n_rows.data_ptr(), fate.data_ptr(), _stream_ptr(self.device)))
-            rows_out[lo:hi] = rows.cpu().numpy()
-            n_rows_out[lo:hi] = n_rows.cpu().numpy()
-            fate_out[lo:hi] = fate.cpu().numpy()
-        return rows_out, n_rows_out, fate_out
+            rows_host[lo:hi].copy_(rows, non_blocking=True)
+            n_rows_host[lo:hi].copy_(n_rows, non_blocking=True)
+            fate_host[lo:hi].copy_(fate, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()   # the device buffers are reused next round
+        return rows_host.numpy(), n_rows_host.numpy(), fate_host.numpy()
 
 
 # ---------------------------------------------------------------------------

@@ -164,12 +164,17 @@ class TrajectorySimulator:
                     torch.distributed.broadcast(s, 0)
                     seed = int(s.item())
             lo, hi = eng.shard_range(total, rank, world)
-            for first in range(lo, hi, self.chunk):
+            for k, first in enumerate(range(lo, hi, self.chunk)):
                 n = min(self.chunk, hi - first)
+                if not save_mask:
+                    # nothing to read back per chunk: alternate streams so consecutive chunks overlap
+                    prop.propagate_philox(source, seed, first, n, slot=k)
+                    continue
                 res = prop.propagate_philox(source, seed, first, n, save_mask=save_mask)
-                if save_mask and res.saved_index.numel():
+                if res.saved_index.numel():
                     ic = prop.draw(source, seed, index=res.saved_index)
                     molecules.extend(self._collect(prop, ic))
+            prop.join()
         else:
             # host draws, replayed: loop l of the reference's N_loops belongs to rank l % world
             batch_v, batch_x, filled = [], [], 0
@@ -225,7 +230,12 @@ class TrajectorySimulator:
         rows, n_rows, fate = prop.trajectories(ic, select=select)
         names = prop.flat.fate_names
         out = []
+        max_rows = rows.shape[1]
         for k in range(rows.shape[0]):
             name = names[int(fate[k])]
-            out.append(Molecule.from_rows(rows[k, : int(n_rows[k])].copy(), name, alive=(name == "Detected")))
+            nk = int(n_rows[k])
+            # full-length trajectories stay views of the (pinned) result block; short ones are copied
+            # out so that a few hits do not keep a mostly empty block alive
+            block = rows[k] if nk == max_rows else rows[k, :nk].copy()
+            out.append(Molecule.from_rows(block, name, alive=(name == "Detected")))
         return out
