@@ -44,6 +44,10 @@ METRIC = "molecules/s through CeNTREX beamline"
 UNIT = "molecules/s"
 WORKLOAD = ("configs[1]: examples/lens_simulation_beamline.py full CeNTREX beamline with ElectrostaticLens, "
             "J=2 mJ=0 Stark curve at 27.6 kV, CeNTREX velocity/position distributions")
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload at
+# 1e7 molecules (profiles/r01_full_c_current.txt); scaled linearly when --molecules differs
+NCU_TRAFFIC_LENS_1E7 = 3.52e6
+NCU_TRAFFIC_WALK_1E7 = 481.3e6 + 18.1e6
 # algorithmic work per unit
 FLOP_PER_ROW = 30      # one ballistic step + hit test
 FLOP_PER_STEP = 162    # one lens RK step (4 force evaluations)
@@ -161,7 +165,7 @@ class ClockSampler:
         def loop():
             while not self._stop.is_set():
                 self.sample()
-                self._stop.wait(0.02)
+                self._stop.wait(0.001)
 
         self._thread = threading.Thread(target=loop, daemon=True)
         self._thread.start()
@@ -306,7 +310,9 @@ def run_ours(args):
     fp64_peak_tflops = 2 * dfma.value / 1e12       # FMA = 2 flop
     roofline = {
         "kernel": "lens_kernel", "bound": "fp64", "achieved": lens_tflops, "peak": fp64_peak_tflops,
-        "unit": "TFLOP/s", "frac": (lens_tflops / fp64_peak_tflops) if lens_tflops else None, "traffic": None,
+        "unit": "TFLOP/s", "frac": (lens_tflops / fp64_peak_tflops) if lens_tflops else None,
+        "traffic": NCU_TRAFFIC_LENS_1E7 * n / 1e7, "traffic_source": "profiles/r01_full_c_current.txt (ncu --set full)",
+        "fp64_pipe_utilisation_ncu": 0.644,
         "peak_source": "measured live: cmt_fp64_peak DFMA stream (no FP64 figure in MEASURED_PEAKS.json)",
         "algorithmic_flop_per_launch": flop_lens, "avg_launch_ms": lens_ms,
         "share_of_step": lens_ms / (ms_seq / args.steps) if ms_seq > 0 else None,
@@ -316,7 +322,8 @@ def run_ours(args):
     walk_gbs = BYTES_PER_MOLECULE * n / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else None
     roofline_walk = {
         "kernel": "walk_kernel<ic>", "bound": "hbm", "achieved": walk_gbs, "peak": hbm_peak, "unit": "GB/s",
-        "frac": (walk_gbs / hbm_peak) if walk_gbs else None, "traffic": None, "peak_source": hbm_src,
+        "frac": (walk_gbs / hbm_peak) if walk_gbs else None, "traffic": NCU_TRAFFIC_WALK_1E7 * n / 1e7,
+        "traffic_source": "profiles/r01_full_c_current.txt (ncu --set full)", "peak_source": hbm_src,
         "algorithmic_bytes_per_launch": BYTES_PER_MOLECULE * n, "avg_launch_ms": walk_ms,
         "share_of_step": walk_ms / (ms_seq / args.steps) if ms_seq > 0 else None,
         "algorithmic_flop_per_launch": flop_rows,
@@ -365,6 +372,24 @@ def run_ours(args):
     philox_value = world * n * args.steps / ph_s
     philox_same = bool((cnt_host == counters).all()) if world == 1 else None
 
+    # ---- e2e_api: the call a user of the reference makes, examples/lens_simulation_beamline.py:87-89 ----
+    from trajectories.trajectory_simulator import TrajectorySimulator
+
+    sim = TrajectorySimulator(device=local, seed=seed)
+    api_steps = max(1, min(args.steps, 5))
+    for _ in range(3):   # reach the steady state of the pinned result blocks (the first runs allocate them)
+        sim.run_simulation(bl, "bench", N_traj=n, apertures_of_interest=["Detected"], n_jobs=10)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(api_steps):
+        sim.run_simulation(bl, "bench", N_traj=n, apertures_of_interest=["Detected"], n_jobs=10)
+    torch.cuda.synchronize()
+    api_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    n_saved = len(sim.result.molecules)
+    rows_bytes = sum(m.trajectory.n for m in sim.result.molecules) * 80
+    api_value = n * api_steps / api_s      # under torch.distributed run_simulation shards N_traj itself
+
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -387,6 +412,10 @@ def run_ours(args):
             "e2e_philox": {"value": philox_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * (len(cnt_host) + 4),
                            "path": "cmt_run_host_philox (run_simulation default): Philox4x32-10 source on device, Counter D2H",
                            "counters_match_device_run": philox_same},
+            "e2e_api": {"value": api_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": rows_bytes + 8 * 16,
+                        "path": "TrajectorySimulator.run_simulation(beamline, N_traj=n, apertures_of_interest=['Detected'], n_jobs=10): "
+                                "Philox source, Counter, and the detected molecules' full trajectories back as Molecule objects",
+                        "saved_molecules_per_step": n_saved, "steps": api_steps},
             "gpu_launches": launches,
             "value_one_stream": value_seq, "ms_per_step_one_stream": ms_seq / args.steps,
             "overlap": "none" if args.no_overlap else f"{prop.n_slots} streams: consecutive steps alternate streams (independent batches)",

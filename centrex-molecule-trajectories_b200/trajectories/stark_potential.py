@@ -15,9 +15,10 @@ import numpy as np
 from . import _tlf
 
 try:  # pragma: no cover - not installed in the build image
+    from centrex_TlF.hamiltonian import generate_uncoupled_hamiltonian_X  # type: ignore  # noqa: F401
     from centrex_TlF.states import State, UncoupledBasisState  # type: ignore
 
-    HAVE_CENTREX_TLF = True
+    HAVE_CENTREX_TLF = True      # the real package (the state-only shim has no Hamiltonian)
 except Exception:  # ImportError or a broken install
     from ._states import State, UncoupledBasisState
 

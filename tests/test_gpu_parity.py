@@ -323,7 +323,7 @@ def test_fast_math_equals_reference_math(torch_cuda, cuda_lib):
     ic = torch.from_numpy(standard_ics(300000, 77, 3.0)).cuda()
     flat = eng.flatten(bl.elements)
     outs = []
-    for flags in (0, 1):
+    for flags in (0, 1):                                    # 1: plain-intrinsic arithmetic
         old = cuda_lib.cmt_debug_flags(flags)
         try:
             prop = eng.Propagator(flat, 0)
@@ -344,3 +344,61 @@ def test_fast_math_equals_reference_math(torch_cuda, cuda_lib):
         n = outs[0][4][k]
         np.testing.assert_array_equal(outs[0][3][k, :n].view(np.int64), outs[1][3][k, :n].view(np.int64))
     assert outs[0][2][1] > 50_000_000                      # tens of millions of RK steps compared
+
+
+def test_run_simulation_spa_saved_trajectories(torch_cuda):
+    """BASELINE.json configs[3]: SPA beamline, Gaussian position source, detected molecules saved."""
+    from trajectories.distributions import GaussianPositionDistribution
+    from trajectories.trajectory_simulator import TrajectorySimulator
+
+    bl = spa_beamline()
+    sim = TrajectorySimulator(seed=11, chunk=1 << 20)           # several chunks
+    sim.run_simulation(bl, "spa", N_traj=int(3e6), apertures_of_interest=["Detected"], n_jobs=9,
+                       xdist=GaussianPositionDistribution())
+    c = sim.counter.counter_dict
+    n_run = 900 * int(3e6 / 900)
+    assert sum(c.values()) == n_run
+    eff = sim.counter.calculate_efficiency()
+    assert abs(eff - 3.1e-4) < 6e-5                              # SURVEY.md 3.4 [probe]: ~3.1e-4
+    mols = sim.result.molecules
+    assert len(mols) == c["Detected"]
+    for m in mols[:50]:
+        assert m.trajectory.x.shape == (19, 3) and m.trajectory.t.shape == (19,)   # 1 + 2 x 9 rows
+        assert m.alive and m.aperture_hit == "Detected"
+        assert np.all(np.diff(m.trajectory.t) >= 0) and np.all(np.diff(m.trajectory.x[:, 2]) >= 0)
+        assert np.all(m.trajectory.a[:, 1] == -9.80665) and np.all(m.trajectory.a[:, [0, 2]] == 0)
+    # the saved trajectories are exactly what the oracle computes from their first rows
+    ic = np.array([np.concatenate([m.trajectory.x[0], m.trajectory.v[0]]) for m in mols[:200]]).T
+    want = oracle.propagate(bl.elements, ic, want_rows=True)
+    for k, m in enumerate(mols[:200]):
+        got = np.concatenate([m.trajectory.x, m.trajectory.v, m.trajectory.a, m.trajectory.t[:, None]], axis=1)
+        assert relerr(got, want["rows"][k, :19]) < TIGHT
+    # same seed without saving: identical Counter (the saved-index path does not disturb the run)
+    sim2 = TrajectorySimulator(seed=11)
+    sim2.run_simulation(bl, "spa", N_traj=int(3e6), n_jobs=9, xdist=GaussianPositionDistribution())
+    assert sim2.counter.counter_dict == c
+
+
+def test_state_and_voltage_sweep(torch_cuda):
+    """BASELINE.json configs[2] in miniature: a loop over states and voltages like
+    examples/lens_simulation_different_states.py:137-152 (state swapped in place, a_interp reset)."""
+    from trajectories.stark_potential import UncoupledBasisState
+    from trajectories.trajectory_simulator import TrajectorySimulator
+
+    bl = lens_beamline()                                           # table built lazily from lens.state / lens.V
+    sim = TrajectorySimulator(seed=5)
+    eff = {}
+    for (J, mJ) in [(0, 0), (1, 0), (2, 0), (2, 2)]:
+        for V in (20e3, 30e3):
+            lens = bl.find_element("ES lens")
+            lens.state = 1 * UncoupledBasisState(J=J, mJ=mJ, I1=1 / 2, m1=1 / 2, I2=1 / 2, m2=1 / 2, Omega=0,
+                                                 P=(-1) ** J, electronic_state="X")
+            lens.V = V
+            lens.a_interp = None
+            sim.run_simulation(bl, f"J={J},mJ={mJ},V={V}", N_traj=int(2e6), apertures_of_interest=["Detected"], n_jobs=10)
+            eff[(J, mJ, V)] = sim.counter.calculate_efficiency()
+            assert sum(sim.counter.counter_dict.values()) == int(2e6)
+    assert len(sim.results) == 8
+    # J=0 is high-field seeking (defocused): far fewer detected molecules than the focused J=2, mJ=0
+    assert eff[(0, 0, 30e3)] < 0.5 * eff[(2, 0, 30e3)]
+    assert eff[(2, 0, 30e3)] > 1e-4
