@@ -402,3 +402,123 @@ def test_state_and_voltage_sweep(torch_cuda):
     # J=0 is high-field seeking (defocused): far fewer detected molecules than the focused J=2, mJ=0
     assert eff[(0, 0, 30e3)] < 0.5 * eff[(2, 0, 30e3)]
     assert eff[(2, 0, 30e3)] > 1e-4
+
+
+def _same_bits_or_close(a, b, tol=TIGHT):
+    """NaN-aware comparison: identical NaN/Inf pattern, finite values within tol."""
+    a, b = np.asarray(a), np.asarray(b)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.array_equal(np.isinf(a), np.isinf(b)) and np.array_equal(np.sign(a[np.isinf(a)]), np.sign(b[np.isinf(b)]))
+    f = np.isfinite(a)
+    if f.any():
+        assert relerr(a[f], b[f]) < tol
+
+
+def test_unusual_beamlines(torch_cuda):
+    """Two lenses in series, a lens first, a lens with a coarse user table on an uneven grid
+    (takes the plain-intrinsic path), overlapping elements, an empty beamline."""
+    from trajectories.beamline import Beamline
+    from trajectories.beamline_elements.apertures import CircularAperture, FieldPlates, RectangularAperture
+    from trajectories.beamline_elements.electrostatic_lens import ElectrostaticLens, make_interpolator
+
+    table = lens_table()
+    ic = standard_ics(40000, 5, 2.5)
+
+    def lens(name, z0, L, tab=table, **kw):
+        return ElectrostaticLens(name=name, z0=z0, L=L, a_interp=make_interpolator(*tab), **kw)
+
+    uneven_r = np.array([0.0, 0.001, 0.0035, 0.004, 0.011, 0.0199, 0.0225])
+    uneven = (uneven_r, -2.0e5 * uneven_r ** 1.1)
+    cases = {
+        "two lenses": [CircularAperture(name="in", z0=0.05, L=0.01, d=0.03), lens("L1", 0.4, 0.3),
+                       FieldPlates(name="fp", z0=0.8, L=0.2, w=0.03), lens("L2", 1.2, 0.25, dz=2e-3),
+                       RectangularAperture(name="out", z0=2.0, L=0.01, w=0.02, h=0.02)],
+        "lens first": [lens("L", 0.1, 0.5), CircularAperture(name="c", z0=1.0, L=0.1, d=0.02)],
+        "uneven table": [CircularAperture(name="in", z0=0.05, L=0.01, d=0.03), lens("L", 0.4, 0.3, tab=uneven)],
+        "overlap": [CircularAperture(name="a", z0=0.10, L=0.30, d=0.03), CircularAperture(name="b", z0=0.20, L=0.05, d=0.02),
+                    RectangularAperture(name="r", z0=0.21, L=0.5, w=0.05, h=0.01)],
+        "lens only, one step": [lens("L", 0.3, 1e-3)],
+    }
+    for name, elems in cases.items():
+        bl = Beamline(elems)
+        want = oracle.propagate(bl.elements, ic)
+        got = gpu_propagate(torch_cuda, bl, ic)
+        np.testing.assert_array_equal(got["fate"], want["fate"], err_msg=name)
+        np.testing.assert_array_equal(got["counters"], want["counters"], err_msg=name)
+        np.testing.assert_array_equal(got["work"][:3], want["work"], err_msg=name)
+        assert relerr(got["fin"], want["fin"]) < TIGHT, name
+        if name == "uneven table":
+            assert got["work"][4] > 0.5 * got["work"][1]     # uneven grids use the plain-intrinsic step
+        # full trajectories of a sample through the same beamline
+        rows, n_rows, fate = got["prop"].trajectories(torch_cuda.from_numpy(np.ascontiguousarray(ic[:, :300])).cuda())
+        w2 = oracle.propagate(bl.elements, ic[:, :300], want_rows=True)
+        np.testing.assert_array_equal(n_rows, w2["n_rows"], err_msg=name)
+        for k in range(300):
+            assert relerr(rows[k, : n_rows[k]], w2["rows"][k, : n_rows[k]]) < TIGHT, name
+    # an empty beamline detects everything and leaves the initial row untouched
+    got = gpu_propagate(torch_cuda, Beamline([]), ic[:, :1000])
+    assert (got["fate"] == 0).all() and got["counters"].tolist() == [1000]
+    np.testing.assert_array_equal(got["fin"][0:6], ic[:, :1000])
+
+
+def test_table_out_of_range_is_counted_and_raised(torch_cuda):
+    """A force evaluation beyond the a_interp table: the reference's interp1d raises ValueError
+    (electrostatic_lens.py:209,217); here it is counted on the device and raised after the run."""
+    from trajectories.beamline import Beamline
+    from trajectories.beamline_elements.electrostatic_lens import ElectrostaticLens, make_interpolator
+    from trajectories.distributions import Distribution
+    from trajectories.trajectory_simulator import TrajectorySimulator
+
+    r = np.linspace(0, 0.006, 30)                      # table ends well inside the 22 mm bore
+    bl = Beamline([ElectrostaticLens(name="L", z0=0.1, L=0.3, a_interp=make_interpolator(r, -1e4 * r))])
+    ic = standard_ics(5000, 3, 5.0)
+    want = oracle.propagate(bl.elements, ic)
+    got = gpu_propagate(torch_cuda, bl, ic)
+    assert want["work"][2] > 0
+    np.testing.assert_array_equal(got["work"][:3], want["work"])       # same count of out-of-range evaluations
+    np.testing.assert_array_equal(got["fate"], want["fate"])
+    assert relerr(got["fin"], want["fin"]) < TIGHT
+
+    class Fixed(Distribution):
+        def __init__(self, data):
+            self.data = data
+
+        def draw(self, n):
+            return self.data[:, :n]
+
+        def save_to_hdf(self, *a, **k):
+            pass
+
+    with pytest.raises(ValueError, match="interpolation range"):
+        TrajectorySimulator().run_simulation(bl, "r", vdist=Fixed(ic[3:6]), xdist=Fixed(ic[0:3]), N_traj=4000)
+
+
+def test_hostile_initial_conditions(torch_cuda):
+    """vz = 0, negative vz, NaN/Inf components, huge and tiny values: the GPU follows the same IEEE
+    comparisons as the reference (e.g. `rho > d/2` is False for NaN), so fates still match the oracle."""
+    bl = lens_beamline(lens_table())
+    base = standard_ics(64, 9, 3.0)
+    ic = np.repeat(base, 12, axis=1)
+    n = ic.shape[1]
+    k = np.arange(n) % 12
+    ic[5, k == 1] = 0.0                      # vz = 0 -> dt = +-inf
+    ic[5, k == 2] *= -1                      # flying backwards: negative dt
+    ic[0, k == 3] = np.nan
+    ic[4, k == 4] = np.inf
+    ic[5, k == 5] = 1e-300                   # dt overflows
+    ic[5, k == 6] = 1e300                    # dt underflows towards 0
+    ic[0, k == 7] = 1e200
+    ic[2, k == 8] = lens_beamline(lens_table()).elements[0].z0      # starts exactly on the first plane: dt == 0
+    ic[3, k == 9] = -0.0
+    ic[1, k == 10] = 5e-324                  # subnormal position
+    ic[5, k == 11] = np.nan
+    want = oracle.propagate(bl.elements, ic)
+    got = gpu_propagate(torch_cuda, bl, ic)
+    np.testing.assert_array_equal(got["fate"], want["fate"])
+    np.testing.assert_array_equal(got["counters"], want["counters"])
+    _same_bits_or_close(got["fin"], want["fin"])
+    ap = apertures_beamline()
+    want = oracle.propagate(ap.elements, ic)
+    got = gpu_propagate(torch_cuda, ap, ic)
+    np.testing.assert_array_equal(got["fate"], want["fate"])
+    _same_bits_or_close(got["fin"], want["fin"])
