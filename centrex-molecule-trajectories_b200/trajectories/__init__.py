@@ -10,8 +10,8 @@ so existing beamline scripts run unchanged:
     from trajectories.beamline_elements.electrostatic_lens import ElectrostaticLens
     from trajectories.trajectory_simulator import TrajectorySimulator
 """
-from . import (beamline, beamline_elements, distributions, molecule, stark_potential,  # noqa: F401
-               trajectory_simulator)
+from . import (beamline, beamline_elements, distributions, molecule, post_processing,  # noqa: F401
+               stark_potential, trajectory_simulator, utils)
 
-__all__ = ["beamline", "beamline_elements", "distributions", "molecule", "stark_potential",
-           "trajectory_simulator"]
+__all__ = ["beamline", "beamline_elements", "distributions", "molecule", "post_processing", "stark_potential",
+           "trajectory_simulator", "utils"]

@@ -17,9 +17,18 @@ class Dataset:
         return self.data[key]
 
 
+class Attrs(dict):
+    """Like h5py: numbers come back as numpy scalars."""
+
+    def __setitem__(self, key, value):
+        if isinstance(value, (bool, int, float)):
+            value = np.asarray(value)[()]
+        super().__setitem__(key, value)
+
+
 class Group:
     def __init__(self):
-        self.attrs = {}
+        self.attrs = Attrs()
         self.children = {}
 
     def _walk(self, path, create=False):

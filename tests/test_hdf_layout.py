@@ -77,3 +77,60 @@ def test_missing_h5py_is_reported(tmp_path, monkeypatch):
     monkeypatch.setitem(sys.modules, "h5py", None)
     with pytest.raises(ImportError, match="h5py"):
         make_result().save_to_hdf(tmp_path / "x.hdf", "r")
+
+
+def test_round_trip_through_utils(h5, tmp_path):
+    """save_to_hdf -> utils.import_sim_result_from_hdf (reference utils.py:149-159)."""
+    from trajectories import utils
+
+    res = make_result()
+    path = tmp_path / "rt.hdf"
+    res.save_to_hdf(path, "run")
+    back = utils.import_sim_result_from_hdf(path, "run")
+    assert back.counter.counter_dict == res.counter.counter_dict
+    assert [type(e).__name__ for e in back.beamline.elements] == [type(e).__name__ for e in res.beamline.elements]
+    for a, b in zip(back.beamline.elements, res.beamline.elements):
+        assert (a.name, a.z0, a.L, a.z1) == (b.name, b.z0, b.L, b.z1)
+    lens = back.beamline.find_element("ES lens")
+    assert lens.V == 27.6e3 and lens.x0 == 0.0 and lens.a_interp is None
+    assert back.xdist == res.xdist and back.vdist == res.vdist
+    assert len(back.molecules) == 2
+    for a, b in zip(back.molecules, res.molecules):
+        np.testing.assert_array_equal(a.trajectory.x, b.trajectory.x)
+        np.testing.assert_array_equal(a.trajectory.t, b.trajectory.t)
+        assert a.aperture_hit == b.aperture_hit and a.alive == b.alive and a.trajectory.n == b.trajectory.n
+
+
+def test_post_processing_at_a_plane():
+    """find_radial_pos_dist / find_vel_dist (reference post_processing.py:20-140)."""
+    from trajectories.molecule import Molecule
+    from trajectories.post_processing import find_radial_pos_dist, find_vel_dist, take_timestep
+    from trajectories.trajectory_simulator import Counter, SimulationResult
+
+    g = 9.80665
+
+    def rows(x0, v0, zs):
+        out, x, v, t = [], np.array(x0, float), np.array(v0, float), 0.0
+        a = np.array([0.0, -g, 0.0])
+        out.append(np.concatenate([x, v, a, [t]]))
+        for z in zs:
+            dt = (z - x[2]) / v[2]
+            x, v = take_timestep(x, v, a, dt)
+            t += dt
+            out.append(np.concatenate([x, v, a, [t]]))
+        return np.array(out)
+
+    m1 = Molecule.from_rows(rows([0.001, 0.0, 0.0], [1.0, 2.0, 200.0], [0.5, 1.0, 2.0]), "Detected", True)
+    m2 = Molecule.from_rows(rows([0.0, 0.002, 0.0], [0.0, 0.0, 100.0], [0.5]), "4K shield", False)
+    res = SimulationResult(Counter(), None, None, None, [m1, m2])
+    at = find_radial_pos_dist(res, 0.75)
+    assert at.shape == (1, 2)                                      # m2 stopped at z = 0.5
+    dt = 0.25 / 200.0                                              # from the stored row at z = 0.5
+    x05, v05 = m1.trajectory.x[1], m1.trajectory.v[1]
+    np.testing.assert_allclose(at[0], [x05[0] + v05[0] * dt, x05[1] + v05[1] * dt - g * dt ** 2 / 2], rtol=1e-12)
+    v = find_vel_dist(res, 0.75)
+    np.testing.assert_allclose(v[0], [1.0, v05[1] - g * dt, 200.0], rtol=1e-12)
+    both = find_radial_pos_dist(res, 0.5)                          # z is a stored row for both
+    assert both.shape == (2, 2) and both[1, 1] == m2.trajectory.x[1, 1]
+    assert find_radial_pos_dist(res, 0.5, elements=["Detected"]).shape == (1, 2)
+    assert find_vel_dist(res, 5.0).shape == (0,)
