@@ -359,7 +359,7 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
     if (has_lens) {
         // persistent lanes: enough CTAs to fill every SM, no more than the queue can feed
         const int64_t max_ctas = (n + LENS_THREADS - 1) / LENS_THREADS;
-        const int grid_lens = (int)std::min<int64_t>(max_ctas, (int64_t)bl->n_sm * 4);
+        const int grid_lens = (int)std::min<int64_t>(max_ctas, (int64_t)bl->n_sm * LENS_MIN_CTAS);
         ScopedTimer tm(1, st);
         lens_kernel<<<grid_lens, LENS_THREADS, bl->tab_bytes, st>>>(bl->P, first_index, *out, Q);
     }
@@ -549,6 +549,8 @@ extern "C" int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t 
     if (n == 0) return CMT_OK;
     std::lock_guard<std::mutex> lk(g_pipe_mu);
     HostPipe &p = g_pipe;
+    // one launch pair per 2^24 molecules: splitting a run further was measured slower (the lens
+    // integrator of a small chunk cannot fill the chip); consecutive chunks alternate streams
     const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 24);
     int rc = pipe_prepare(p, bl, chunk, false, false, false);
     if (rc) return rc;

@@ -178,7 +178,10 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
 // ---------------------------------------------------------------------------
 // lens kernel: persistent lanes, per-lane state machine
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(LENS_THREADS)
+#ifndef LENS_MIN_CTAS
+#define LENS_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(LENS_THREADS, LENS_MIN_CTAS)
 lens_kernel(const __grid_constant__ Params P, int64_t first_index,
             const __grid_constant__ cmt_outputs_t O, Queue Q)
 {

@@ -223,7 +223,7 @@ class Propagator:
     runs beside the walk kernel of chunk i+1.  `join()` makes the current stream wait for them.
     """
 
-    def __init__(self, elements_or_flat, device=None, n_slots: int = 2):
+    def __init__(self, elements_or_flat, device=None, n_slots: int = 3):
         self.flat = elements_or_flat if isinstance(elements_or_flat, FlatBeamline) else flatten(elements_or_flat)
         self.device = resolve_device(device)
         self.dev = device_beamline(self.flat, self.device)

@@ -164,8 +164,9 @@ class TrajectorySimulator:
                     torch.distributed.broadcast(s, 0)
                     seed = int(s.item())
             lo, hi = eng.shard_range(total, rank, world)
-            for k, first in enumerate(range(lo, hi, self.chunk)):
-                n = min(self.chunk, hi - first)
+            chunk = self.chunk
+            for k, first in enumerate(range(lo, hi, chunk)):
+                n = min(chunk, hi - first)
                 if not save_mask:
                     # nothing to read back per chunk: alternate streams so consecutive chunks overlap
                     prop.propagate_philox(source, seed, first, n, slot=k)
