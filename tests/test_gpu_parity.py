@@ -522,3 +522,79 @@ def test_hostile_initial_conditions(torch_cuda):
     got = gpu_propagate(torch_cuda, ap, ic)
     np.testing.assert_array_equal(got["fate"], want["fate"])
     _same_bits_or_close(got["fin"], want["fin"])
+
+
+def test_full_size_properties(torch_cuda):
+    """BASELINE.json configs[1] at full size (1e7 molecules): size-independent checks."""
+    from trajectories import _engine as eng
+    from trajectories.distributions import CeNTREXPositionDistribution, CeNTREXVelocityDistribution
+
+    torch = torch_cuda
+    bl = lens_beamline(lens_table())
+    n = 10_000_000
+    prop = eng.Propagator(bl.elements, 0)
+    src = eng.make_source(CeNTREXVelocityDistribution(), CeNTREXPositionDistribution())
+    names = prop.flat.fate_names
+    # (1) the source run and the replay of the same samples agree molecule by molecule
+    prop.reset()
+    a = prop.propagate_philox(src, 77, 5_000_000_000, n, want_fate=True)
+    fate_a, cnt_a = a.fate.clone(), a.counters.clone()
+    ic = prop.draw(src, 77, 5_000_000_000, n)
+    prop.reset()
+    b = prop.propagate_ic(ic, first_index=5_000_000_000, want_fate=True, want_final=True,
+                          save_mask=1 << names.index("Detected"))
+    assert torch.equal(fate_a, b.fate) and torch.equal(cnt_a, b.counters)
+    # (2) the Counter is the histogram of the fate bytes and sums to N
+    hist = torch.bincount(b.fate.long(), minlength=len(names))
+    assert torch.equal(hist, b.counters) and int(b.counters.sum()) == n
+    # (3) the saved-index list is exactly the detected molecules, sorted, in global numbering
+    det = torch.nonzero(b.fate == names.index("Detected")).flatten() + 5_000_000_000
+    assert torch.equal(det, b.saved_index)
+    # (4) geometry of the final rows: every fate ends on the plane (or wall) that defines it
+    fin = b.final
+    els = {e.name: e for e in bl.elements}
+    sel = b.fate == names.index("Detected")
+    assert torch.allclose(fin[2, sel], torch.full_like(fin[2, sel], els["DR aperture"].z1), rtol=0, atol=1e-12)
+    assert bool((fin[0, sel].abs() < 0.009).all()) and bool((fin[1, sel].abs() < 0.015).all())
+    sel = b.fate == names.index("Lens entrance")
+    assert torch.allclose(fin[2, sel], torch.full_like(fin[2, sel], els["ES lens"].z0), rtol=0, atol=1e-12)
+    assert bool((torch.hypot(fin[0, sel], fin[1, sel]) > els["ES lens"].d / 2).all())
+    sel = b.fate == names.index("Inside lens")
+    assert bool((torch.hypot(fin[0, sel], fin[1, sel]) > els["ES lens"].d / 2).all())
+    assert bool((fin[2, sel] > els["ES lens"].z0).all()) and bool((fin[2, sel] < els["ES lens"].z1 + 1e-9).all())
+    assert bool((fin[6, sel] != 0).any())                       # the stored a is the lens force l1, not (0,-g,0)
+    sel = b.fate == names.index("Field plates")
+    on_wall = (fin[0, sel].abs() - 0.01).abs() < 1e-12          # stopped where it crossed a plate ...
+    at_entry = (fin[2, sel] - els["Field plates"].z0).abs() < 1e-12   # ... or was outside at z0
+    assert bool((on_wall | at_entry).all())
+    # (5) time and energy bookkeeping: t > 0, vz untouched, vy = vy0 - g t outside the lens
+    never_lens = b.fate < names.index("Inside lens")
+    assert bool((fin[9] > 0).all()) and torch.equal(fin[5], ic[5])
+    vy_pred = ic[4, never_lens] - 9.80665 * fin[9, never_lens]
+    assert float((fin[4, never_lens] - vy_pred).abs().max()) < 1e-12
+    # (6) work counters: rows + steps account for every trajectory row
+    w = b.work.cpu().numpy()
+    assert w[3] == int(b.counters[names.index("Inside lens"):].sum())      # lens entries = everything after the entrance
+    assert w[2] == 0 and w[4] == 0
+
+
+def test_hit_fractions_match_the_reference(torch_cuda, golden_dir):
+    """Per-element hit fractions of an independent Philox run agree with the fractions of the
+    reference's own run (golden std sets, 12 000 molecules) within Monte Carlo error."""
+    from trajectories.trajectory_simulator import TrajectorySimulator
+
+    ref_counts, names = None, None
+    for seed in (0, 1, 2):
+        g = np.load(golden_dir / f"std_seed{seed}.npz")
+        names = list(g["lens_fate_names"])
+        c = np.bincount(g["lens_fate"], minlength=len(names))
+        ref_counts = c if ref_counts is None else ref_counts + c
+    n_ref = ref_counts.sum()
+    bl = lens_beamline((g["table_r"], g["table_a"]))
+    sim = TrajectorySimulator(seed=123)
+    sim.run_simulation(bl, "r", N_traj=int(2e7), n_jobs=10)
+    n = sum(sim.counter.counter_dict.values())
+    for k, name in enumerate(names):
+        p = sim.counter.counter_dict.get(name, 0) / n             # 2e7 molecules: essentially the true fraction
+        sigma = np.sqrt(max(p * (1 - p), 1e-12) / n_ref)
+        assert abs(ref_counts[k] / n_ref - p) < 4.5 * sigma + 1.5 / n_ref, (name, ref_counts[k] / n_ref, p)
