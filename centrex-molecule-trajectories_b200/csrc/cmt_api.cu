@@ -176,6 +176,31 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
         }
     }
 
+    // leading run of circular planes for the walk kernel's tight loop
+    {
+        FastPlanes &F = P.fast;
+        F.n = 0; F.next_element = 0; F.ends_at_lens = 0;
+        int e = 0;
+        while (e < n_elements && P.el[e].type == CMT_CIRCULAR && F.n + 2 <= CMT_MAX_FAST_PLANES) {
+            for (int k = 0; k < 2; ++k) {
+                F.z[F.n] = k == 0 ? P.el[e].z0 : P.el[e].z1;
+                F.T[F.n] = P.el[e].p[0];
+                F.fate[F.n] = P.el[e].fate;
+                ++F.n;
+            }
+            ++e;
+        }
+        if (e < n_elements && e == P.first_lens && F.n + 1 <= CMT_MAX_FAST_PLANES) {
+            F.z[F.n] = P.el[e].z0;
+            F.T[F.n] = P.el[e].p[0];
+            F.fate[F.n] = P.el[e].fate;     // "Lens entrance"
+            ++F.n;
+            F.ends_at_lens = 1;
+            ++e;
+        }
+        F.next_element = e;
+    }
+
     bl->tab_bytes = (size_t)tab_total * sizeof(double4);
     if (tab_total > 0) {
         std::vector<double4> h((size_t)tab_total);

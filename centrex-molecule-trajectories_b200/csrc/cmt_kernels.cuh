@@ -143,18 +143,30 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
         int fate = -1;
         bool to_lens = false;
         if (valid) {
-            for (int e = 0; e < n_walk; ++e) {
-                const DevElement &E = P.el[e];
-                if (E.type == CMT_LENS) {
-                    to_plane(m, E.z0, P.g, rec);
-                    if (outside_radius(m, E.p[0])) fate = E.fate;   // "Lens entrance"
-                    else to_lens = true;
-                    break;
-                }
-                fate = do_aperture(E, m, P.g, rec);
-                if (fate >= 0) break;
+            // leading circular planes: tight loop, no element dispatch
+#pragma unroll 1
+            for (int p = 0; p < P.fast.n; ++p) {
+                to_plane(m, P.fast.z[p], P.g, rec);
+                if (outside_radius(m, P.fast.T[p])) { fate = P.fast.fate[p]; break; }
             }
-            if (fate < 0 && !to_lens) fate = P.fate_detected;
+            if (fate < 0) {
+                if (P.fast.ends_at_lens) {
+                    to_lens = true;
+                } else {
+                    for (int e = P.fast.next_element; e < n_walk; ++e) {
+                        const DevElement &E = P.el[e];
+                        if (E.type == CMT_LENS) {
+                            to_plane(m, E.z0, P.g, rec);
+                            if (outside_radius(m, E.p[0])) fate = E.fate;   // "Lens entrance"
+                            else to_lens = true;
+                            break;
+                        }
+                        fate = do_aperture(E, m, P.g, rec);
+                        if (fate >= 0) break;
+                    }
+                    if (fate < 0 && !to_lens) fate = P.fate_detected;
+                }
+            }
         }
         rows_total += rec.n;
         entries += to_lens ? 1u : 0u;
