@@ -431,12 +431,14 @@ extern "C" int cmt_philox_draw(const cmt_source_t *src, uint64_t seed, int64_t f
 
 extern "C" int cmt_trajectories(const cmt_beamline_t *bl, int64_t n, const double *state, int n_comp,
                                 int64_t state_ld, const int64_t *select, int64_t select_base, double *rows,
-                                int32_t max_rows, int32_t *n_rows, uint8_t *fate, void *stream)
+                                int32_t max_rows, const int64_t *row_offset, int32_t *n_rows, uint8_t *fate,
+                                void *stream)
 {
     if (!bl) return fail(CMT_EINVAL, "beamline handle is NULL");
     if (n < 0) return fail(CMT_EINVAL, "n < 0");
     if (n == 0) return CMT_OK;
-    if (!state || !rows) return fail(CMT_EINVAL, "state/rows is NULL");
+    if (!state) return fail(CMT_EINVAL, "state is NULL");
+    if (!rows && !n_rows && !fate) return fail(CMT_EINVAL, "nothing to compute: rows, n_rows and fate are all NULL");
     if (n_comp != 6 && n_comp != 10) return fail(CMT_EINVAL, "n_comp must be 6 or 10");
     if (max_rows < 1) return fail(CMT_EINVAL, "max_rows < 1");
     cudaStream_t st = (cudaStream_t)stream;
@@ -445,7 +447,7 @@ extern "C" int cmt_trajectories(const cmt_beamline_t *bl, int64_t n, const doubl
     {
         ScopedTimer tm(2, st);
         trajectory_kernel<<<grid, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, n, state, n_comp, state_ld, select,
-                                                                      select_base, rows, max_rows, n_rows, fate);
+                                                                      select_base, rows, max_rows, row_offset, n_rows, fate);
     }
     CUDA_TRY(cudaGetLastError());
     return CMT_OK;

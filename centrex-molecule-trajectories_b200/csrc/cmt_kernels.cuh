@@ -313,8 +313,8 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
 __global__ void __launch_bounds__(TRAJ_THREADS)
 trajectory_kernel(const __grid_constant__ Params P, int64_t n, const double *__restrict__ state, int n_comp,
                   int64_t state_ld, const int64_t *__restrict__ select, int64_t select_base,
-                  double *__restrict__ rows, int max_rows, int32_t *__restrict__ n_rows,
-                  uint8_t *__restrict__ fate_out)
+                  double *__restrict__ rows, int max_rows, const int64_t *__restrict__ row_offset,
+                  int32_t *__restrict__ n_rows, uint8_t *__restrict__ fate_out)
 {
     extern __shared__ double4 smem_tab[];
     for (int i = threadIdx.x; i < P.tab_total; i += blockDim.x) smem_tab[i] = P.tab[i];
@@ -333,7 +333,9 @@ trajectory_kernel(const __grid_constant__ Params P, int64_t n, const double *__r
         m.t = state[9 * state_ld + col];
     }
     WriteRows rec;
-    rec.base = rows + (size_t)j * max_rows * CMT_ROW_DOUBLES;
+    // rows == nullptr: count only; row_offset: compact layout (molecule j starts at row row_offset[j])
+    rec.base = rows == nullptr ? nullptr
+               : rows + (size_t)(row_offset ? row_offset[j] : j * (int64_t)max_rows) * CMT_ROW_DOUBLES;
     rec.max_rows = max_rows;
     rec.row(m);  // Molecule.init_trajectory stores the initial row, molecule.py:24
 

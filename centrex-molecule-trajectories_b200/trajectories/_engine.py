@@ -354,38 +354,61 @@ class Propagator:
                                                 ic.data_ptr(), max(n, 1), _stream_ptr(self.device)))
         return ic
 
+    def _traj_call(self, m, state, n_comp, sel, select_base, rows_ptr, row_offset_ptr, n_rows, fate):
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().cmt_trajectories(
+                self.dev.handle, m, state.data_ptr(), n_comp, state.stride(0), sel, int(select_base), rows_ptr,
+                self.dev.max_rows, row_offset_ptr, n_rows.data_ptr(), fate.data_ptr(), _stream_ptr(self.device)))
+
     def trajectories(self, state, select=None, select_base=0):
-        """Full rows for the molecules in `state` ([6|10, m] device tensor), optionally
-        gathered through `select` (global indices, device int64).  Returns host arrays
-        (rows [k, max_rows, 10] valid up to n_rows[k], n_rows [k], fate [k]).  The rows land
-        in pinned host memory straight from the device (no pageable staging copy)."""
+        """Full trajectories of the molecules in `state` ([6|10, m] device tensor), optionally gathered
+        through `select` (global indices, device int64).
+
+        Two passes per batch: a counting call gives every molecule's row count, an exclusive scan turns
+        the counts into row offsets, and the second call writes the rows compactly, so memory is
+        sum(n_rows) x 80 B whatever the fates are (a molecule stopped by the first aperture has 2 rows,
+        a detected one 613).  Rows go to pinned host memory straight from the device.
+
+        Returns (rows [total_rows, 10], offsets [k + 1] int64, fate [k]) as host arrays; molecule j owns
+        rows[offsets[j]:offsets[j + 1]].
+        """
         torch = _torch()
         n_comp = state.shape[0]
         k_total = select.numel() if select is not None else state.shape[1]
-        max_rows = self.dev.max_rows
-        per = max(1, min(k_total, ROW_BUDGET_BYTES // (max_rows * nat.CMT_ROW_DOUBLES * 8)))
-        rows_host = torch.empty((k_total, max_rows, nat.CMT_ROW_DOUBLES), dtype=torch.float64, pin_memory=True)
-        n_rows_host = torch.empty(k_total, dtype=torch.int32, pin_memory=True)
-        fate_host = torch.empty(k_total, dtype=torch.uint8, pin_memory=True)
-        for lo in range(0, k_total, per):
-            hi = min(k_total, lo + per)
-            m = hi - lo
-            rows = torch.empty((m, max_rows, nat.CMT_ROW_DOUBLES), dtype=torch.float64, device=self.tdev)
-            n_rows = torch.empty(m, dtype=torch.int32, device=self.tdev)
-            fate = torch.empty(m, dtype=torch.uint8, device=self.tdev)
+        row_budget = max(self.dev.max_rows, ROW_BUDGET_BYTES // (nat.CMT_ROW_DOUBLES * 8))
+
+        # pass 1: counts and fates for everything
+        n_rows = torch.empty(k_total, dtype=torch.int32, device=self.tdev)
+        fate = torch.empty(k_total, dtype=torch.uint8, device=self.tdev)
+        if k_total:
+            sel_ptr = select.data_ptr() if select is not None else None
+            self._traj_call(k_total, state, n_comp, sel_ptr, select_base, None, None, n_rows, fate)
+        offsets = torch.zeros(k_total + 1, dtype=torch.int64, device=self.tdev)
+        torch.cumsum(n_rows, 0, out=offsets[1:])
+        offsets_host = offsets.cpu()
+        total_rows = int(offsets_host[-1])
+        rows_host = torch.empty((total_rows, nat.CMT_ROW_DOUBLES), dtype=torch.float64, pin_memory=total_rows > 0)
+
+        # pass 2: rows, in batches bounded by the device row budget
+        lo = 0
+        off_np = offsets_host.numpy()
+        while lo < k_total:
+            hi = int(np.searchsorted(off_np, off_np[lo] + row_budget, side="right")) - 1
+            hi = min(max(hi, lo + 1), k_total)
+            base, n_batch_rows = int(off_np[lo]), int(off_np[hi] - off_np[lo])
+            rows = torch.empty((max(n_batch_rows, 1), nat.CMT_ROW_DOUBLES), dtype=torch.float64, device=self.tdev)
+            rel = offsets[lo:hi] - base
             if select is not None:
-                sel_ptr, st_ptr = select[lo:hi].data_ptr(), state.data_ptr()
+                sel_ptr, st = select[lo:hi].data_ptr(), state
             else:
-                sel_ptr, st_ptr = None, state[:, lo:hi].data_ptr()
-            with torch.cuda.device(self.device):
-                nat.check(nat.lib().cmt_trajectories(self.dev.handle, m, st_ptr, n_comp, state.stride(0), sel_ptr,
-                                                     int(select_base), rows.data_ptr(), max_rows,
-                                                     n_rows.data_ptr(), fate.data_ptr(), _stream_ptr(self.device)))
-            rows_host[lo:hi].copy_(rows, non_blocking=True)
-            n_rows_host[lo:hi].copy_(n_rows, non_blocking=True)
-            fate_host[lo:hi].copy_(fate, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()   # the device buffers are reused next round
-        return rows_host.numpy(), n_rows_host.numpy(), fate_host.numpy()
+                sel_ptr, st = None, state[:, lo:hi]
+            self._traj_call(hi - lo, st, n_comp, sel_ptr, select_base, rows.data_ptr(), rel.data_ptr(),
+                            n_rows[lo:hi], fate[lo:hi])
+            rows_host[base:base + n_batch_rows].copy_(rows[:n_batch_rows], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()   # the device buffer is reused next round
+            lo = hi
+        return rows_host.numpy(), off_np, fate.cpu().numpy()
 
 
 # ---------------------------------------------------------------------------

@@ -75,7 +75,8 @@ _SIGNATURES = {
     "cmt_philox_draw": (C.c_int, [C.POINTER(Source), C.c_uint64, C.c_int64, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_int64, C.c_void_p]),
     "cmt_trajectories": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
-                                   C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                   C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
     "cmt_run_host_ic": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
     "cmt_run_host_philox": (C.c_int, [C.c_void_p, C.POINTER(Source), C.c_uint64, C.c_int64, C.c_int64,

@@ -24,9 +24,8 @@ def propagate_molecule(elements, molecule, mark_detected: bool) -> None:
     state[0:3, 0], state[3:6, 0], state[6:9, 0], state[9, 0] = tr.x[last], tr.v[last], tr.a[last], tr.t[last]
     if state[8, 0] != 0.0:
         raise ValueError("a_z != 0 is not supported on the GPU path")
-    rows, n_rows, fate = prop.trajectories(torch.from_numpy(state).to(prop.tdev))
-    k = int(n_rows[0])
-    tr.extend_rows(rows[0, 1:k])          # row 0 repeats the molecule's current row
+    rows, offsets, fate = prop.trajectories(torch.from_numpy(state).to(prop.tdev))
+    tr.extend_rows(rows[1:int(offsets[1])])   # row 0 repeats the molecule's current row
     name = prop.flat.fate_names[int(fate[0])]
     if name == "Detected":
         if mark_detected:

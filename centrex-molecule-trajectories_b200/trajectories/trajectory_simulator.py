@@ -228,15 +228,11 @@ class TrajectorySimulator:
     # -- helpers ----------------------------------------------------------------
     @staticmethod
     def _collect(prop: "eng.Propagator", ic, select=None) -> List[Molecule]:
-        rows, n_rows, fate = prop.trajectories(ic, select=select)
+        rows, offsets, fate = prop.trajectories(ic, select=select)
         names = prop.flat.fate_names
         out = []
-        max_rows = rows.shape[1]
-        for k in range(rows.shape[0]):
+        for k in range(len(fate)):
             name = names[int(fate[k])]
-            nk = int(n_rows[k])
-            # full-length trajectories stay views of the (pinned) result block; short ones are copied
-            # out so that a few hits do not keep a mostly empty block alive
-            block = rows[k] if nk == max_rows else rows[k, :nk].copy()
-            out.append(Molecule.from_rows(block, name, alive=(name == "Detected")))
+            # each trajectory is a view of its slice of the (pinned) result block
+            out.append(Molecule.from_rows(rows[offsets[k]:offsets[k + 1]], name, alive=(name == "Detected")))
         return out

@@ -161,12 +161,15 @@ int cmt_philox_draw(const cmt_source_t *src, uint64_t seed, int64_t first_index,
  * n_comp = 6 (x,v; a and t default) or 10 (x,v,a,t: resume from an arbitrary
  * row, which is what BeamlineElement.propagate_through(molecule) needs).
  * select (device, optional): molecule j reads column select[j] - select_base.
- * rows:   [n][max_rows][10] device; rows past n_rows[j] are left untouched.
- * first_element..: elements [first_element, n_elements) are walked. */
+ * rows:   device, or NULL to only count rows and report fates.  Without row_offset the
+ *         layout is [n][max_rows][10] (rows past n_rows[j] are left untouched); with
+ *         row_offset (device int64 [n], e.g. the exclusive scan of a counting call's n_rows)
+ *         molecule j writes its rows compactly from row row_offset[j] on.
+ * max_rows bounds the rows written per molecule; n_rows[j] always reports the full count. */
 int cmt_trajectories(const cmt_beamline_t *bl, int64_t n, const double *state, int n_comp,
                      int64_t state_ld, const int64_t *select, int64_t select_base,
-                     double *rows, int32_t max_rows, int32_t *n_rows, uint8_t *fate,
-                     void *stream);
+                     double *rows, int32_t max_rows, const int64_t *row_offset, int32_t *n_rows,
+                     uint8_t *fate, void *stream);
 
 /* ---- host-buffer convenience (what a non-CUDA host language binds) ------ */
 

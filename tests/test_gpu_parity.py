@@ -80,20 +80,32 @@ def test_golden_trajectory_rows(torch_cuda, golden_dir):
     prop = eng.Propagator(bl.elements, 0)
     idx = g["lens_row_idx"]
     ic = torch.from_numpy(np.ascontiguousarray(g["ic"][:, idx])).cuda()
-    rows, n_rows, fate = prop.trajectories(ic)
+    rows, offs, fate = prop.trajectories(ic)
+    n_rows = np.diff(offs)
     off = g["lens_row_off"]
     for k in range(len(idx)):
         want = g["lens_rows"][off[k]:off[k + 1]]
         assert n_rows[k] == want.shape[0] == g["lens_n_rows"][idx[k]]
         assert fate[k] == g["lens_fate"][idx[k]]
-        assert relerr(rows[k, : n_rows[k]], want) < TIGHT
+        assert relerr(rows[offs[k]:offs[k + 1]], want) < TIGHT
+    assert rows.shape == (int(n_rows.sum()), 10)               # compact: no padding rows
     # select path: gather by global index out of the full IC array
     full = torch.from_numpy(np.ascontiguousarray(g["ic"])).cuda()
     sel = torch.from_numpy(idx.astype(np.int64) + 1000).cuda()
-    rows2, n_rows2, fate2 = prop.trajectories(full, select=sel, select_base=1000)
-    np.testing.assert_array_equal(n_rows2, n_rows)
-    for k in range(len(idx)):
-        np.testing.assert_array_equal(rows2[k, : n_rows[k]], rows[k, : n_rows[k]])
+    rows2, offs2, fate2 = prop.trajectories(full, select=sel, select_base=1000)
+    np.testing.assert_array_equal(offs2, offs)
+    np.testing.assert_array_equal(rows2, rows)
+    np.testing.assert_array_equal(fate2, fate)
+    # batching: a tiny device row budget forces many batches and must give the same rows
+    import trajectories._engine as engmod
+    old_budget = engmod.ROW_BUDGET_BYTES
+    engmod.ROW_BUDGET_BYTES = 2000 * 80
+    try:
+        rows3, offs3, fate3 = prop.trajectories(full, select=sel, select_base=1000)
+    finally:
+        engmod.ROW_BUDGET_BYTES = old_budget
+    np.testing.assert_array_equal(offs3, offs)
+    np.testing.assert_array_equal(rows3, rows)
 
 
 @pytest.mark.parametrize("n,seed,sigma", [(200000, 11, 39.5), (60000, 12, 4.0), (257, 13, 4.0), (1, 14, 4.0), (33, 15, 1.0)])
@@ -330,9 +342,9 @@ def test_fast_math_equals_reference_math(torch_cuda, cuda_lib):
             prop.dev = eng.DeviceBeamline(flat, 0)          # bypass the handle cache: flags are read at creation
             prop.reset()
             res = prop.propagate_ic(ic, want_fate=True, want_final=True)
-            rows, n_rows, fate = prop.trajectories(ic[:, :2000].contiguous())
+            rows, offs, fate = prop.trajectories(ic[:, :2000].contiguous())
             torch.cuda.synchronize()
-            outs.append((res.fate.cpu().numpy(), res.final.cpu().numpy(), res.work.cpu().numpy(), rows, n_rows))
+            outs.append((res.fate.cpu().numpy(), res.final.cpu().numpy(), res.work.cpu().numpy(), rows, offs))
         finally:
             cuda_lib.cmt_debug_flags(old)
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
@@ -340,9 +352,7 @@ def test_fast_math_equals_reference_math(torch_cuda, cuda_lib):
     np.testing.assert_array_equal(outs[0][2][:4], outs[1][2][:4])
     assert outs[0][2][4] == 0 and outs[1][2][4] == outs[1][2][1]     # RK steps on the plain-intrinsic path: none / all
     np.testing.assert_array_equal(outs[0][4], outs[1][4])
-    for k in range(2000):
-        n = outs[0][4][k]
-        np.testing.assert_array_equal(outs[0][3][k, :n].view(np.int64), outs[1][3][k, :n].view(np.int64))
+    np.testing.assert_array_equal(outs[0][3].view(np.int64), outs[1][3].view(np.int64))
     assert outs[0][2][1] > 50_000_000                      # tens of millions of RK steps compared
 
 
@@ -450,11 +460,11 @@ def test_unusual_beamlines(torch_cuda):
         if name == "uneven table":
             assert got["work"][4] > 0.5 * got["work"][1]     # uneven grids use the plain-intrinsic step
         # full trajectories of a sample through the same beamline
-        rows, n_rows, fate = got["prop"].trajectories(torch_cuda.from_numpy(np.ascontiguousarray(ic[:, :300])).cuda())
+        rows, offs, fate = got["prop"].trajectories(torch_cuda.from_numpy(np.ascontiguousarray(ic[:, :300])).cuda())
         w2 = oracle.propagate(bl.elements, ic[:, :300], want_rows=True)
-        np.testing.assert_array_equal(n_rows, w2["n_rows"], err_msg=name)
+        np.testing.assert_array_equal(np.diff(offs), w2["n_rows"], err_msg=name)
         for k in range(300):
-            assert relerr(rows[k, : n_rows[k]], w2["rows"][k, : n_rows[k]]) < TIGHT, name
+            assert relerr(rows[offs[k]:offs[k + 1]], w2["rows"][k, : w2["n_rows"][k]]) < TIGHT, name
     # an empty beamline detects everything and leaves the initial row untouched
     got = gpu_propagate(torch_cuda, Beamline([]), ic[:, :1000])
     assert (got["fate"] == 0).all() and got["counters"].tolist() == [1000]
@@ -598,3 +608,23 @@ def test_hit_fractions_match_the_reference(torch_cuda, golden_dir):
         p = sim.counter.counter_dict.get(name, 0) / n             # 2e7 molecules: essentially the true fraction
         sigma = np.sqrt(max(p * (1 - p), 1e-12) / n_ref)
         assert abs(ref_counts[k] / n_ref - p) < 4.5 * sigma + 1.5 / n_ref, (name, ref_counts[k] / n_ref, p)
+
+
+def test_saving_an_early_fate_is_compact(torch_cuda):
+    """Saving molecules that die at the first aperture (2-3 rows each, half of all molecules) must not
+    allocate 613 rows per molecule."""
+    from trajectories.trajectory_simulator import TrajectorySimulator
+
+    bl = lens_beamline(lens_table())
+    sim = TrajectorySimulator(seed=2)
+    sim.run_simulation(bl, "r", N_traj=400_000, apertures_of_interest=["4K shield", "Detected"], n_jobs=10)
+    c = sim.counter.counter_dict
+    mols = sim.result.molecules
+    assert len(mols) == c["4K shield"] + c.get("Detected", 0)
+    n_rows = np.array([m.trajectory.x.shape[0] for m in mols])
+    hit = np.array([m.aperture_hit == "4K shield" for m in mols])
+    assert set(n_rows[hit]) <= {2, 3} and (n_rows[~hit] == 613).all()
+    for m in mols[:100]:
+        assert not m.alive and m.trajectory.t.shape == (m.trajectory.x.shape[0],)
+        r = np.hypot(*m.trajectory.x[-1, :2])
+        assert r > 0.0127                                             # it ended outside the 1-inch aperture

@@ -36,7 +36,7 @@ def test_abi_argument_validation(cuda_lib):
     assert cuda_lib.cmt_beamline_create(None, 0, None, 0, 0, 0, 9.80665, 0, C.byref(out)) == -1
     assert cuda_lib.cmt_beamline_create(None, 41, None, 0, 2, 1, 9.80665, 0, C.byref(out)) == -1
     assert cuda_lib.cmt_propagate_ic(None, 1, 0, None, 1, None, None, 0, None) == -1
-    assert cuda_lib.cmt_trajectories(None, 1, None, 6, 1, None, 0, None, 1, None, None, None) == -1
+    assert cuda_lib.cmt_trajectories(None, 1, None, 6, 1, None, 0, None, 1, None, None, None, None) == -1
     assert cuda_lib.cmt_workspace_bytes(None, 10) == 0
     assert cuda_lib.cmt_beamline_max_rows(None) == -1
     cuda_lib.cmt_beamline_destroy(None)
