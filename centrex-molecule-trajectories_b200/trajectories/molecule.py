@@ -1,8 +1,10 @@
-"""Molecule / Trajectory containers (reference molecule.py:8-186).
+"""Molecule / Trajectory containers (API of the reference's molecule.py:8-186).
 
-On the GPU path a molecule is nine FP64 registers; these classes are the host
+On the GPU path a molecule is ten FP64 registers; these classes are the host
 view of a finished (or hand-built) trajectory: `x`, `v`, `a` are (n,3) float64
-arrays, `t` is (n,), exactly what post-processing and the HDF layout expect.
+arrays and `t` is (n,), which is what post-processing and the HDF layout
+expect.  Trajectories that come back from the GPU are zero-copy views of one
+[n,10] row block (columns x,y,z,vx,vy,vz,ax,ay,az,t).
 """
 from __future__ import annotations
 
@@ -11,115 +13,141 @@ from dataclasses import dataclass
 import numpy as np
 
 g = 9.80665  # scipy.constants.g
+_DEFAULT_A = np.array((0, -g, 0))
+
+
+class Trajectory:
+    """Row store: one row per recorded point, `n` rows in use."""
+
+    __slots__ = ("x", "v", "a", "t", "n")
+
+    def __init__(self, beamline=None, n_rows: int = None):
+        if n_rows is None:
+            # the reference sizes the arrays as 10 spare rows + every element's N_steps()
+            n_rows = 10 + sum(element.N_steps() for element in beamline.elements)
+        self._allocate(n_rows)
+        self.n = 0
+
+    def _allocate(self, n_rows: int) -> None:
+        nan = np.nan
+        self.x, self.v, self.a = (np.full((n_rows, 3), nan) for _ in range(3))
+        self.t = np.full(n_rows, nan)
+
+    @classmethod
+    def from_rows(cls, rows: np.ndarray) -> "Trajectory":
+        """Zero-copy view of a row block [n,10]."""
+        tr = object.__new__(cls)
+        tr.x, tr.v, tr.a, tr.t = rows[:, 0:3], rows[:, 3:6], rows[:, 6:9], rows[:, 9]
+        tr.n = rows.shape[0]
+        return tr
+
+    def as_rows(self) -> np.ndarray:
+        """The used rows as one [n,10] block."""
+        k = self.n
+        return np.concatenate([self.x[:k], self.v[:k], self.a[:k], self.t[:k, None]], axis=1)
+
+    def _grow(self, extra: int) -> None:
+        pad3, pad1 = np.full((extra, 3), np.nan), np.full(extra, np.nan)
+        self.x, self.v, self.a = (np.concatenate((arr, pad3)) for arr in (self.x, self.v, self.a))
+        self.t = np.concatenate((self.t, pad1))
+
+    def update(self, x, v, a, t) -> None:
+        """Append one row."""
+        if self.n == self.t.shape[0]:
+            self._grow(max(16, self.n))
+        k = self.n
+        self.x[k], self.v[k], self.a[k], self.t[k] = x, v, a, t
+        self.n = k + 1
+
+    def extend_rows(self, rows: np.ndarray) -> None:
+        """Append a block of GPU-produced rows [k,10]."""
+        k = rows.shape[0]
+        short = self.n + k - self.t.shape[0]
+        if short > 0:
+            self._grow(short)
+        where = slice(self.n, self.n + k)
+        self.x[where], self.v[where], self.a[where], self.t[where] = rows[:, 0:3], rows[:, 3:6], rows[:, 6:9], rows[:, 9]
+        self.n += k
+
+    def add_steps(self, beamline) -> None:
+        self._grow(sum(element.N_steps() for element in beamline.elements))
+
+    def drop_nans(self) -> None:
+        """Trim the unused (NaN) tail of every array."""
+        keep3 = lambda arr: arr[np.isfinite(arr).all(axis=1)]  # noqa: E731
+        self.x, self.v, self.a = keep3(self.x), keep3(self.v), keep3(self.a)
+        self.t = self.t[np.isfinite(self.t)]
+
+    def save_to_hdf(self, file, run_name: str, group_name: str) -> None:
+        """Datasets x, v, a, t under <run>/<group> (reference layout)."""
+        self.drop_nans()
+        group = file.create_group(run_name + "/" + group_name)
+        for key in ("x", "v", "a", "t"):
+            group.create_dataset(key, data=getattr(self, key))
 
 
 @dataclass
 class Molecule:
     alive: bool = True
 
-    def init_trajectory(self, beamline, x0=np.array((0, 0, 0)), v0=np.array((0, 0, 200)),
-                        a0=np.array((0, -g, 0)), t0=0):
+    # -- construction ---------------------------------------------------------
+    def init_trajectory(self, beamline, x0=np.array((0, 0, 0)), v0=np.array((0, 0, 200)), a0=_DEFAULT_A, t0=0):
         self.trajectory = Trajectory(beamline)
         self.trajectory.update(x0, v0, a0, t0)
 
-    # kinematics of the last row (molecule.py:26-56); `not delta_t` covers None and 0
-    def x(self, delta_t: float = None):
-        if not delta_t:
-            return self.trajectory.x[self.trajectory.n - 1, :]
-        return self.x() + self.v() * delta_t + self.a() * delta_t ** 2 / 2
+    @classmethod
+    def from_rows(cls, rows: np.ndarray, aperture_hit: str, alive: bool) -> "Molecule":
+        """Wrap GPU-produced rows [n,10]."""
+        mol = cls(alive=alive)
+        mol.trajectory = Trajectory.from_rows(rows)
+        mol.aperture_hit = aperture_hit
+        return mol
 
-    def v(self, delta_t: float = None):
-        if not delta_t:
-            return self.trajectory.v[self.trajectory.n - 1, :]
-        return self.v() + self.a() * delta_t
+    # -- state of the last recorded point --------------------------------------
+    def _last(self, name: str):
+        tr = self.trajectory
+        return getattr(tr, name)[tr.n - 1]
 
     def a(self):
-        return self.trajectory.a[self.trajectory.n - 1, :]
+        return self._last("a")
 
     def t(self):
-        return self.trajectory.t[self.trajectory.n - 1]
+        return self._last("t")
 
-    def update_trajectory(self, delta_t, a=np.array((0, -g, 0))):
-        x, v, t = self.x(delta_t), self.v(delta_t), self.t() + delta_t
-        self.trajectory.update(x, v, a, t)
+    def x(self, delta_t: float = None):
+        """Position now, or after a further ballistic flight of delta_t (falsy delta_t: now)."""
+        here = self._last("x")
+        if not delta_t:
+            return here
+        return here + self._last("v") * delta_t + self._last("a") * delta_t ** 2 / 2
 
+    def v(self, delta_t: float = None):
+        """Velocity now, or after a further ballistic flight of delta_t."""
+        now = self._last("v")
+        if not delta_t:
+            return now
+        return now + self._last("a") * delta_t
+
+    def update_trajectory(self, delta_t, a=_DEFAULT_A):
+        """Record the point reached after delta_t; the new row stores `a` (default gravity)."""
+        self.trajectory.update(self.x(delta_t), self.v(delta_t), a, self.t() + delta_t)
+
+    # -- fate -----------------------------------------------------------------
     def set_aperture_hit(self, aperture_name):
         self.aperture_hit = aperture_name
 
     def set_dead(self):
         self.alive = False
 
+    # -- output ---------------------------------------------------------------
     def plot_trajectory(self, axes):
-        color = {"Detected": "g", "Field plates": "r"}.get(self.aperture_hit, "k")
-        axes[0].plot(self.trajectory.x[:, 2], self.trajectory.x[:, 0], c=color)
-        axes[1].plot(self.trajectory.x[:, 2], self.trajectory.x[:, 1], c=color)
+        colour = {"Detected": "g", "Field plates": "r"}.get(self.aperture_hit, "k")
+        xs = self.trajectory.x
+        axes[0].plot(xs[:, 2], xs[:, 0], c=colour)
+        axes[1].plot(xs[:, 2], xs[:, 1], c=colour)
 
     def save_to_hdf(self, file, run_name: str, group_name: str):
         self.trajectory.save_to_hdf(file, run_name, group_name)
-        grp = file[run_name + "/" + group_name]
-        grp.attrs["aperture_hit"] = self.aperture_hit
-        grp.attrs["alive"] = self.alive
-
-    @classmethod
-    def from_rows(cls, rows: np.ndarray, aperture_hit: str, alive: bool) -> "Molecule":
-        """Wrap GPU-produced rows [n,10] = x,y,z,vx,vy,vz,ax,ay,az,t."""
-        m = cls(alive=alive)
-        m.trajectory = Trajectory.from_rows(rows)
-        m.aperture_hit = aperture_hit
-        return m
-
-
-class Trajectory:
-    def __init__(self, beamline=None, n_rows: int = None):
-        if n_rows is None:
-            n_rows = 10 + sum(e.N_steps() for e in beamline.elements)   # molecule.py:117-121
-        self.x = np.full((n_rows, 3), np.nan)
-        self.v = np.full((n_rows, 3), np.nan)
-        self.a = np.full((n_rows, 3), np.nan)
-        self.t = np.full((n_rows,), np.nan)
-        self.n = 0
-
-    @classmethod
-    def from_rows(cls, rows: np.ndarray) -> "Trajectory":
-        rows = np.ascontiguousarray(rows, dtype=np.float64)
-        tr = cls.__new__(cls)
-        tr.x, tr.v, tr.a, tr.t = rows[:, 0:3], rows[:, 3:6], rows[:, 6:9], rows[:, 9]
-        tr.n = rows.shape[0]
-        return tr
-
-    def update(self, x, v, a, t):
-        if self.n >= self.t.shape[0]:
-            self._grow(max(16, self.n))
-        self.x[self.n, :], self.v[self.n, :], self.a[self.n, :], self.t[self.n] = x, v, a, t
-        self.n += 1
-
-    def extend_rows(self, rows: np.ndarray):
-        """Append GPU-produced rows [k,10]."""
-        k = rows.shape[0]
-        if self.n + k > self.t.shape[0]:
-            self._grow(self.n + k - self.t.shape[0])
-        s = slice(self.n, self.n + k)
-        self.x[s], self.v[s], self.a[s], self.t[s] = rows[:, 0:3], rows[:, 3:6], rows[:, 6:9], rows[:, 9]
-        self.n += k
-
-    def _grow(self, extra: int):
-        self.x = np.concatenate((self.x, np.full((extra, 3), np.nan)))
-        self.v = np.concatenate((self.v, np.full((extra, 3), np.nan)))
-        self.a = np.concatenate((self.a, np.full((extra, 3), np.nan)))
-        self.t = np.concatenate((self.t, np.full((extra,), np.nan)))
-
-    def add_steps(self, beamline):
-        self._grow(sum(e.N_steps() for e in beamline.elements))
-
-    def drop_nans(self):
-        self.x = self.x[np.all(np.isfinite(self.x), axis=1), :]
-        self.v = self.v[np.all(np.isfinite(self.v), axis=1), :]
-        self.a = self.a[np.all(np.isfinite(self.a), axis=1), :]
-        self.t = self.t[np.isfinite(self.t)]
-
-    def save_to_hdf(self, file, run_name: str, group_name: str) -> None:
-        self.drop_nans()
-        path = run_name + "/" + group_name
-        file.create_group(path)
-        for key in ("x", "v", "a", "t"):
-            file[path].create_dataset(key, data=getattr(self, key))
+        attrs = file[run_name + "/" + group_name].attrs
+        attrs["aperture_hit"] = self.aperture_hit
+        attrs["alive"] = self.alive
