@@ -165,7 +165,7 @@ class ClockSampler:
         def loop():
             while not self._stop.is_set():
                 self.sample()
-                self._stop.wait(0.001)
+                self._stop.wait(0.004)
 
         self._thread = threading.Thread(target=loop, daemon=True)
         self._thread.start()
@@ -262,6 +262,16 @@ def run_ours(args):
     # ---- pass B (the headline value): the same K steps, consecutive steps on alternating streams so
     # that the lens integrator of one batch overlaps the walk kernel of the next ----
     slots = [None] * args.steps if args.no_overlap else [k % prop.n_slots for k in range(args.steps)]
+    graphs = None
+    if not args.no_overlap and not args.no_graphs:
+        # one CUDA graph per stream (header memset + walk + lens): a replay is a single host-side launch
+        graphs = [prop.capture_ic(ic, first_index=first, want_fate=True, slot=s) for s in range(prop.n_slots)]
+
+        def step(slot=None, _plain=step):                      # noqa: F811
+            if slot is None:
+                return _plain(None)
+            graphs[slot].replay()
+            return res
     for k in range(warm):
         step(slots[k % len(slots)])
     prop.join()
@@ -418,7 +428,8 @@ def run_ours(args):
                         "saved_molecules_per_step": n_saved, "steps": api_steps},
             "gpu_launches": launches,
             "value_one_stream": value_seq, "ms_per_step_one_stream": ms_seq / args.steps,
-            "overlap": "none" if args.no_overlap else f"{prop.n_slots} streams: consecutive steps alternate streams (independent batches)",
+            "overlap": "none" if args.no_overlap else f"{prop.n_slots} streams: consecutive steps alternate streams (independent batches)"
+                       + ("" if graphs is None else "; each step replays a CUDA graph (memset + walk + lens)"),
             "roofline": roofline, "roofline_walk": roofline_walk,
             "cpu_baseline": cpu,
             "clocks": clocks,
@@ -443,6 +454,7 @@ def main():
     ap.add_argument("--molecules", type=float, default=1e7, help="molecules per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap", action="store_true", help="issue every step on one stream")
+    ap.add_argument("--no-graphs", action="store_true", help="launch the overlapped steps individually instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -214,6 +214,18 @@ class PropagateResult:
     fate_names: List[str] = field(default_factory=list)
 
 
+class GraphedStep:
+    """A captured propagation step: `replay()` enqueues it on its stream."""
+
+    def __init__(self, graph, stream, fate, keep):
+        self.graph, self.stream, self.fate, self._keep = graph, stream, fate, keep
+
+    def replay(self):
+        torch = _torch()
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+
+
 class Propagator:
     """Reusable launch context: beamline handle + scratch buffers on one device.
 
@@ -341,6 +353,25 @@ class Propagator:
                                                      ws.numel(), _stream_ptr(self.device)))
             saved = self._finish_saved(save_mask, saved_buf, L.index)
         return PropagateResult(self.counters, self.work, fate, final, saved, self.flat.fate_names)
+
+    def capture_ic(self, ic, first_index=0, want_fate=True, slot=0) -> "GraphedStep":
+        """Capture one propagate_ic call (header memset + walk + lens kernels) into a CUDA graph on
+        the slot's stream.  Replaying it costs one graph launch on the host instead of three
+        launches plus the Python call path, which matters when a step lasts well under a
+        millisecond and several processes share the host cores."""
+        torch = _torch()
+        assert ic.dtype == torch.float64 and ic.dim() == 2 and ic.shape[0] == 6 and ic.is_cuda and ic.stride(1) == 1
+        n = ic.shape[1]
+        index = slot % self.n_slots
+        st = self._slot_stream(slot)
+        ws = self._workspace(n, index)
+        O, fate, _ = self._outputs(n, want_fate, False, 0, None, index)
+        st.wait_stream(torch.cuda.current_stream(self.device))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.device(self.device), torch.cuda.graph(graph, stream=st):
+            nat.check(nat.lib().cmt_propagate_ic(self.dev.handle, n, int(first_index), ic.data_ptr(), ic.stride(0),
+                                                 C.byref(O), ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+        return GraphedStep(graph, st, fate, (ic, ws, O))
 
     def draw(self, source: nat.Source, seed: int, first_index: int = 0, n: int = 0, index=None):
         """Materialise source samples as a device tensor [6, n]."""
