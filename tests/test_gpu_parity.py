@@ -628,3 +628,37 @@ def test_saving_an_early_fate_is_compact(torch_cuda):
         assert not m.alive and m.trajectory.t.shape == (m.trajectory.x.shape[0],)
         r = np.hypot(*m.trajectory.x[-1, :2])
         assert r > 0.0127                                             # it ended outside the 1-inch aperture
+
+
+def test_graph_replay_and_stream_slots(torch_cuda):
+    """A step captured into a CUDA graph, and steps issued on the private stream slots, give
+    exactly what the plain call on the current stream gives."""
+    from trajectories import _engine as eng
+
+    torch = torch_cuda
+    bl = lens_beamline(lens_table())
+    ic = torch.from_numpy(standard_ics(500_000, 41, 6.0)).cuda()
+    prop = eng.Propagator(bl.elements, 0)
+    prop.reset()
+    ref = prop.propagate_ic(ic, want_fate=True)
+    torch.cuda.synchronize()
+    fate_ref, cnt_ref, work_ref = ref.fate.clone(), ref.counters.clone(), ref.work.clone()
+    # stream slots
+    prop.reset()
+    outs = [prop.propagate_ic(ic, want_fate=True, slot=k) for k in range(6)]
+    prop.join()
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o.fate, fate_ref)
+    assert torch.equal(prop.counters, 6 * cnt_ref) and torch.equal(prop.work, 6 * work_ref)
+    # graph replay
+    prop.reset()
+    steps = [prop.capture_ic(ic, want_fate=True, slot=s) for s in range(prop.n_slots)]
+    prop.reset()                                   # capture itself does not run the kernels, but be explicit
+    for k in range(7):
+        steps[k % len(steps)].replay()
+    prop.join()
+    torch.cuda.synchronize()
+    for s in steps:
+        assert torch.equal(s.fate, fate_ref)
+    assert torch.equal(prop.counters, 7 * cnt_ref) and torch.equal(prop.work, 7 * work_ref)
