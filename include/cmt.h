@@ -24,8 +24,10 @@
  *   - a beamline handle is immutable after creation: concurrent launches on
  *     different streams are safe as long as each uses its own workspace and
  *     output buffers;
- *   - all arithmetic is IEEE-754 binary64 in the reference's operation order
- *     (no fused multiply-add on the path that decides fates).
+ *   - all arithmetic is IEEE-754 binary64 in the reference's operation order;
+ *     fused multiply-adds and shared reciprocals appear only where the result
+ *     is bit-identical to the separately rounded form (csrc/cmt_device.cuh,
+ *     checked on the device by cmt_selftest).
  */
 #ifndef CMT_H
 #define CMT_H
