@@ -233,6 +233,6 @@ class TrajectorySimulator:
         out = []
         for k in range(len(fate)):
             name = names[int(fate[k])]
-            # each trajectory is a view of its slice of the (pinned) result block
+            # each trajectory is a view of its slice of the result block
             out.append(Molecule.from_rows(rows[offsets[k]:offsets[k + 1]], name, alive=(name == "Detected")))
         return out
