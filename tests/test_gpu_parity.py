@@ -662,3 +662,25 @@ def test_graph_replay_and_stream_slots(torch_cuda):
     for s in steps:
         assert torch.equal(s.fate, fate_ref)
     assert torch.equal(prop.counters, 7 * cnt_ref) and torch.equal(prop.work, 7 * work_ref)
+
+
+def test_integration_stub_from_the_docs(torch_cuda):
+    """The ctypes stub printed in INTEGRATION.md (what a maintainer of the reference would add)
+    is executable as written and reproduces the oracle."""
+    import re
+    from pathlib import Path
+
+    from trajectories import _native
+
+    root = Path(__file__).resolve().parent.parent
+    text = (root / "INTEGRATION.md").read_text()
+    block = re.search(r"```python\n# trajectories/_cmt.py.*?\n(.*?)```", text, re.S).group(1)
+    block = block.replace('C.CDLL("libcmt_b200.so")', f'C.CDLL("{_native.LIB_PATH}")')
+    ns = {}
+    exec(compile(block, "INTEGRATION.md:_cmt.py", "exec"), ns)
+    bl = lens_beamline(lens_table())
+    ic = standard_ics(30000, 8, 4.0)
+    fate, counts = ns["propagate"](bl, ic[0:3], ic[3:6])
+    want = oracle.propagate(bl.elements, ic)
+    np.testing.assert_array_equal(fate, want["fate"])
+    assert counts == {nm: int(c) for nm, c in zip(want["fate_names"], want["counters"]) if c}
