@@ -38,6 +38,23 @@ static int fail(int code, const char *fmt, ...)
                         __FILE__, __LINE__);                                                \
     } while (0)
 
+// Entry points run on the handle's device but leave the caller's current device as they found it
+// (PyTorch and other runtimes in the same process read it back with cudaGetDevice).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t status;
+    explicit DeviceGuard(int device)
+    {
+        cudaGetDevice(&prev);
+        status = prev == device ? cudaSuccess : cudaSetDevice(device);
+        if (prev == device) prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 extern "C" const char *cmt_last_error(void) { return g_err; }
 
 static int g_debug_flags = 0;
@@ -222,7 +239,8 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
             }
         }
         if (bl->tab_bytes > 200 * 1024) { delete bl; return fail(CMT_EINVAL, "lens tables too large for shared memory (%zu B)", bl->tab_bytes); }
-        cudaError_t e = cudaSetDevice(device);
+        DeviceGuard guard(device);
+        cudaError_t e = guard.status;
         if (e == cudaSuccess) e = cudaMalloc(&bl->d_tab, bl->tab_bytes);
         if (e == cudaSuccess) e = cudaMemcpy(bl->d_tab, h.data(), bl->tab_bytes, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
@@ -244,7 +262,7 @@ extern "C" void cmt_beamline_destroy(cmt_beamline_t *bl)
 {
     if (!bl) return;
     if (bl->d_tab) {
-        cudaSetDevice(bl->device);
+        DeviceGuard guard(bl->device);
         cudaFree(bl->d_tab);
     }
     delete bl;
@@ -358,7 +376,8 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
                     (long long)n);
     if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return fail(CMT_EINVAL, "workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaSetDevice(bl->device));
+    DeviceGuard guard(bl->device);
+    CUDA_TRY(guard.status);
 
     Queue Q;
     Q.count = reinterpret_cast<unsigned long long *>(workspace);
@@ -442,7 +461,8 @@ extern "C" int cmt_trajectories(const cmt_beamline_t *bl, int64_t n, const doubl
     if (n_comp != 6 && n_comp != 10) return fail(CMT_EINVAL, "n_comp must be 6 or 10");
     if (max_rows < 1) return fail(CMT_EINVAL, "max_rows < 1");
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaSetDevice(bl->device));
+    DeviceGuard guard(bl->device);
+    CUDA_TRY(guard.status);
     const int grid = (int)((n + TRAJ_THREADS - 1) / TRAJ_THREADS);
     {
         ScopedTimer tm(2, st);
@@ -474,7 +494,7 @@ struct HostPipe {
     void release()
     {
         if (device < 0) return;
-        cudaSetDevice(device);
+        DeviceGuard guard(device);
         for (int k = 0; k < 2; ++k) {
             if (st[k]) cudaStreamDestroy(st[k]);
             cudaFree(d_ic[k]); cudaFree(d_fate[k]); cudaFree(d_final[k]); cudaFree(d_ws[k]);
@@ -499,7 +519,6 @@ int pipe_prepare(HostPipe &p, const cmt_beamline_t *bl, int64_t chunk, bool want
     const bool keep_ic = want_ic || p.d_ic[0], keep_fate = want_fate || p.d_fate[0], keep_final = want_final || p.d_final[0];
     chunk = std::max(chunk, p.device == bl->device ? p.chunk : (int64_t)0);
     p.release();
-    CUDA_TRY(cudaSetDevice(bl->device));
     p.device = bl->device;
     p.chunk = chunk;
     p.ws_bytes = std::max(ws, cmt_workspace_bytes(bl, chunk));
@@ -535,6 +554,8 @@ extern "C" int cmt_run_host_ic(const cmt_beamline_t *bl, int64_t n, const double
     if (n == 0) return CMT_OK;
     if (!ic_host) return fail(CMT_EINVAL, "ic_host is NULL");
     std::lock_guard<std::mutex> lk(g_pipe_mu);
+    DeviceGuard guard(bl->device);
+    CUDA_TRY(guard.status);
     HostPipe &p = g_pipe;
     const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 21);
     int rc = pipe_prepare(p, bl, chunk, true, fate_host != nullptr, final_host != nullptr);
@@ -575,6 +596,8 @@ extern "C" int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t 
     if (!counters_host || !src) return fail(CMT_EINVAL, "NULL argument");
     if (n == 0) return CMT_OK;
     std::lock_guard<std::mutex> lk(g_pipe_mu);
+    DeviceGuard guard(bl->device);
+    CUDA_TRY(guard.status);
     HostPipe &p = g_pipe;
     // one launch pair per 2^24 molecules: splitting a run further was measured slower (the lens
     // integrator of a small chunk cannot fill the chip); consecutive chunks alternate streams
@@ -603,7 +626,8 @@ extern "C" int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t 
 extern "C" int cmt_selftest(int device, int64_t n, uint64_t seed, int mode, int64_t out[5])
 {
     if (!out || n < 0 || mode < 0 || mode > 2) return fail(CMT_EINVAL, "bad selftest arguments");
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    CUDA_TRY(guard.status);
     unsigned long long *d = nullptr;
     CUDA_TRY(cudaMalloc(&d, 5 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMemset(d, 0, 5 * sizeof(unsigned long long)));
@@ -623,7 +647,8 @@ extern "C" int cmt_selftest(int device, int64_t n, uint64_t seed, int mode, int6
 // ---------------------------------------------------------------------------
 extern "C" int cmt_fp64_peak(int device, double *dfma_per_s, double *dadd_per_s)
 {
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    CUDA_TRY(guard.status);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     double *d_out = nullptr;

@@ -448,6 +448,9 @@ def test_unusual_beamlines(torch_cuda):
         "overlap": [CircularAperture(name="a", z0=0.10, L=0.30, d=0.03), CircularAperture(name="b", z0=0.20, L=0.05, d=0.02),
                     RectangularAperture(name="r", z0=0.21, L=0.5, w=0.05, h=0.01)],
         "lens only, one step": [lens("L", 0.3, 1e-3)],
+        # 2500 points = 80 kB of shared memory: needs the opt-in dynamic shared-memory limit
+        "fine table": [CircularAperture(name="in", z0=0.05, L=0.01, d=0.03),
+                       lens("L", 0.4, 0.3, tab=(np.linspace(0, 0.0225, 2500), -3.0e4 * np.linspace(0, 0.0225, 2500) ** 0.9))],
     }
     for name, elems in cases.items():
         bl = Beamline(elems)
