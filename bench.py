@@ -302,6 +302,50 @@ def run_ours(args):
     value = world * n * args.steps / (ms * 1e-3)
     value_seq = world * n * args.steps / (ms_seq * 1e-3)
 
+    # ---- the opt-in contracted arithmetic (fused multiply-adds, reciprocal multiplications): same
+    # workload, same two passes, reported beside the default; not the headline ----
+    contracted = None
+    if not args.no_contracted:
+        propc = eng.Propagator(bl.elements, local, math="contracted")
+        for _ in range(warm):
+            propc.reset()
+            resc = propc.propagate_ic(ic, first_index=first, want_fate=True)
+        torch.cuda.synchronize()
+        cnt_c1 = resc.counters.cpu().numpy().copy()
+        lib.cmt_timing_enable(1)
+        lib.cmt_timing_read(None, None, 1)
+        propc.reset()
+        for _ in range(args.steps):
+            propc.propagate_ic(ic, first_index=first, want_fate=True)
+        torch.cuda.synchronize()
+        msc_k = (C.c_double * 4)()
+        nc_k = (C.c_int64 * 4)()
+        lib.cmt_timing_read(msc_k, nc_k, 1)
+        lib.cmt_timing_enable(0)
+        gc = [propc.capture_ic(ic, first_index=first, want_fate=True, slot=s_) for s_ in range(propc.n_slots)]
+        for k in range(warm):
+            gc[k % len(gc)].replay()
+        propc.join()
+        barrier()
+        propc.reset()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for k in range(args.steps):
+            gc[k % len(gc)].replay()
+        propc.join()
+        c1.record()
+        torch.cuda.synchronize()
+        barrier()
+        ms_c = max_over_ranks(c0.elapsed_time(c1))
+        lens_c = msc_k[1] / max(nc_k[1], 1)
+        contracted = {
+            "value": world * n * args.steps / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c / args.steps,
+            "kernel_ms_per_step": {"walk": msc_k[0] / max(nc_k[0], 1), "lens": lens_c},
+            "fates_differing_from_default": int(np.abs(cnt_c1 - counters1).sum() // 2),
+            "note": "TrajectorySimulator(math='contracted'): same algorithm, relaxed roundings; final rows agree with "
+                    "the reference to ~1e-13 relative (tests assert 1e-9), fates can differ only within that distance of an edge",
+        }
+
     # ---- roofline ----
     dfma, dadd = C.c_double(), C.c_double()
     nat.check(lib.cmt_fp64_peak(local, C.byref(dfma), C.byref(dadd)))
@@ -426,6 +470,7 @@ def run_ours(args):
                         "path": "TrajectorySimulator.run_simulation(beamline, N_traj=n, apertures_of_interest=['Detected'], n_jobs=10): "
                                 "Philox source, Counter, and the detected molecules' full trajectories back as Molecule objects",
                         "saved_molecules_per_step": n_saved, "steps": api_steps},
+            "contracted_math": contracted,
             "gpu_launches": launches,
             "value_one_stream": value_seq, "ms_per_step_one_stream": ms_seq / args.steps,
             "overlap": "none" if args.no_overlap else f"{prop.n_slots} streams: consecutive steps alternate streams (independent batches)"
@@ -454,6 +499,7 @@ def main():
     ap.add_argument("--molecules", type=float, default=1e7, help="molecules per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap", action="store_true", help="issue every step on one stream")
+    ap.add_argument("--no-contracted", action="store_true", help="skip the contracted-arithmetic pass")
     ap.add_argument("--no-graphs", action="store_true", help="launch the overlapped steps individually instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":

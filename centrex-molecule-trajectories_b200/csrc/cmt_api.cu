@@ -74,6 +74,7 @@ struct cmt_beamline {
     int device;
     int max_rows;
     int n_sm;
+    int math;           // CMT_MATH_EXACT / CMT_MATH_CONTRACTED
     double4 *d_tab;     // [tab_total]: (r_j, r_{j+1}, a_j, slope_j)
     size_t tab_bytes;   // dynamic shared memory the lens/trajectory kernels need
 };
@@ -148,6 +149,7 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
     bl->device = device;
     bl->n_sm = prop.multiProcessorCount;
     bl->max_rows = 1;
+    bl->math = CMT_MATH_EXACT;
     bl->d_tab = nullptr;
 
     for (int i = 0; i < n_elements; ++i) {
@@ -250,8 +252,10 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
         }
         P.tab = bl->d_tab;
         if (bl->tab_bytes > 40 * 1024) {
-            cudaFuncSetAttribute(lens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
-            cudaFuncSetAttribute(trajectory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            cudaFuncSetAttribute(lens_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            cudaFuncSetAttribute(lens_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            cudaFuncSetAttribute(trajectory_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            cudaFuncSetAttribute(trajectory_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
         }
     }
     *out = bl;
@@ -266,6 +270,14 @@ extern "C" void cmt_beamline_destroy(cmt_beamline_t *bl)
         cudaFree(bl->d_tab);
     }
     delete bl;
+}
+
+extern "C" int cmt_beamline_set_math(cmt_beamline_t *bl, int mode)
+{
+    if (!bl) return fail(CMT_EINVAL, "beamline handle is NULL");
+    if (mode != CMT_MATH_EXACT && mode != CMT_MATH_CONTRACTED) return fail(CMT_EINVAL, "unknown math mode %d", mode);
+    bl->math = mode;
+    return CMT_OK;
 }
 
 extern "C" int cmt_beamline_max_rows(const cmt_beamline_t *bl) { return bl ? bl->max_rows : CMT_EINVAL; }
@@ -394,18 +406,27 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
     const int grid_walk = (int)std::min<int64_t>(tiles, (int64_t)bl->n_sm * 8);
     {
         ScopedTimer tm(0, st);
-        if (philox)
-            walk_kernel<true><<<grid_walk, WALK_THREADS, 0, st>>>(bl->P, S, seed, nullptr, 0, n, first_index, *out, Q);
+        const bool contract = bl->math == CMT_MATH_CONTRACTED;
+        if (philox && contract)
+            walk_kernel<true, true><<<grid_walk, WALK_THREADS, 0, st>>>(bl->P, S, seed, nullptr, 0, n, first_index, *out, Q);
+        else if (philox)
+            walk_kernel<true, false><<<grid_walk, WALK_THREADS, 0, st>>>(bl->P, S, seed, nullptr, 0, n, first_index, *out, Q);
+        else if (contract)
+            walk_kernel<false, true><<<grid_walk, WALK_THREADS, 0, st>>>(bl->P, S, seed, ic, ic_ld, n, first_index, *out, Q);
         else
-            walk_kernel<false><<<grid_walk, WALK_THREADS, 0, st>>>(bl->P, S, seed, ic, ic_ld, n, first_index, *out, Q);
+            walk_kernel<false, false><<<grid_walk, WALK_THREADS, 0, st>>>(bl->P, S, seed, ic, ic_ld, n, first_index, *out, Q);
     }
     CUDA_TRY(cudaGetLastError());
     if (has_lens) {
         // persistent lanes: enough CTAs to fill every SM, no more than the queue can feed
         const int64_t max_ctas = (n + LENS_THREADS - 1) / LENS_THREADS;
-        const int grid_lens = (int)std::min<int64_t>(max_ctas, (int64_t)bl->n_sm * LENS_MIN_CTAS);
+        const int ctas_per_sm = bl->math == CMT_MATH_CONTRACTED ? LENS_MIN_CTAS_CONTRACTED : LENS_MIN_CTAS;
+        const int grid_lens = (int)std::min<int64_t>(max_ctas, (int64_t)bl->n_sm * ctas_per_sm);
         ScopedTimer tm(1, st);
-        lens_kernel<<<grid_lens, LENS_THREADS, bl->tab_bytes, st>>>(bl->P, first_index, *out, Q);
+        if (bl->math == CMT_MATH_CONTRACTED)
+            lens_kernel<true><<<grid_lens, LENS_THREADS, bl->tab_bytes, st>>>(bl->P, first_index, *out, Q);
+        else
+            lens_kernel<false><<<grid_lens, LENS_THREADS, bl->tab_bytes, st>>>(bl->P, first_index, *out, Q);
     }
     CUDA_TRY(cudaGetLastError());
     return CMT_OK;
@@ -466,8 +487,12 @@ extern "C" int cmt_trajectories(const cmt_beamline_t *bl, int64_t n, const doubl
     const int grid = (int)((n + TRAJ_THREADS - 1) / TRAJ_THREADS);
     {
         ScopedTimer tm(2, st);
-        trajectory_kernel<<<grid, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, n, state, n_comp, state_ld, select,
-                                                                      select_base, rows, max_rows, row_offset, n_rows, fate);
+        if (bl->math == CMT_MATH_CONTRACTED)
+            trajectory_kernel<true><<<grid, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, n, state, n_comp, state_ld, select,
+                                                                               select_base, rows, max_rows, row_offset, n_rows, fate);
+        else
+            trajectory_kernel<false><<<grid, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, n, state, n_comp, state_ld, select,
+                                                                                select_base, rows, max_rows, row_offset, n_rows, fate);
     }
     CUDA_TRY(cudaGetLastError());
     return CMT_OK;

@@ -108,7 +108,7 @@ __device__ __forceinline__ void retire(bool done, int fate, const Mol &m, int64_
 // ---------------------------------------------------------------------------
 // walk kernel
 // ---------------------------------------------------------------------------
-template <bool PHILOX>
+template <bool PHILOX, bool CONTRACT>
 __global__ void __launch_bounds__(WALK_THREADS)
 walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source_t S, uint64_t seed,
             const double *__restrict__ ic, int64_t ic_ld, int64_t n, int64_t first_index,
@@ -137,9 +137,9 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
         } else {
             m.x = m.y = m.z = m.vx = m.vy = 0.0; m.vz = 1.0;
         }
-        mol_begin(m, P.g);
+        mol_begin<CONTRACT>(m, P.g);
 
-        CountRows rec;
+        CountRowsT<CONTRACT> rec;
         int fate = -1;
         bool to_lens = false;
         if (valid) {
@@ -147,7 +147,7 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
 #pragma unroll 1
             for (int p = 0; p < P.fast.n; ++p) {
                 to_plane(m, P.fast.z[p], P.g, rec);
-                if (outside_radius(m, P.fast.T[p])) { fate = P.fast.fate[p]; break; }
+                if (outside_radius<CONTRACT>(m, P.fast.T[p])) { fate = P.fast.fate[p]; break; }
             }
             if (fate < 0) {
                 if (P.fast.ends_at_lens) {
@@ -157,7 +157,7 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
                         const DevElement &E = P.el[e];
                         if (E.type == CMT_LENS) {
                             to_plane(m, E.z0, P.g, rec);
-                            if (outside_radius(m, E.p[0])) fate = E.fate;   // "Lens entrance"
+                            if (outside_radius<CONTRACT>(m, E.p[0])) fate = E.fate;   // "Lens entrance"
                             else to_lens = true;
                             break;
                         }
@@ -191,9 +191,13 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
 // lens kernel: persistent lanes, per-lane state machine
 // ---------------------------------------------------------------------------
 #ifndef LENS_MIN_CTAS
-#define LENS_MIN_CTAS 4
+#define LENS_MIN_CTAS 4            // exact arithmetic: 122 registers; 5 or 6 CTAs/SM spill and measured slower
 #endif
-__global__ void __launch_bounds__(LENS_THREADS, LENS_MIN_CTAS)
+#ifndef LENS_MIN_CTAS_CONTRACTED
+#define LENS_MIN_CTAS_CONTRACTED 4
+#endif
+template <bool CONTRACT>
+__global__ void __launch_bounds__(LENS_THREADS, CONTRACT ? LENS_MIN_CTAS_CONTRACTED : LENS_MIN_CTAS)
 lens_kernel(const __grid_constant__ Params P, int64_t first_index,
             const __grid_constant__ cmt_outputs_t O, Queue Q)
 {
@@ -216,6 +220,7 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
     int step = -1;          // >= 0: RK steps already taken inside lens e
     int n_steps = 0;        // of lens e
     double bore_T = 0.0;    // of lens e
+    double r_last = 0.0;    // last abscissa of its table (contracted mode)
     bool have = false;
     bool drained = false;   // warp-uniform: the queue has nothing left
     Table tb;
@@ -240,13 +245,14 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
                         m.vx = q[3 * Q.cap]; m.vy = q[4 * Q.cap]; m.vz = q[5 * Q.cap];
                         const double t = q[6 * Q.cap];
                         local = __double_as_longlong(q[7 * Q.cap]);
-                        mol_begin(m, P.g);
+                        mol_begin<CONTRACT>(m, P.g);
                         m.t = t;
                         e = P.first_lens;
                         const DevElement &E = P.el[e];
                         step = 0; n_steps = E.n_steps; bore_T = E.p[0];
                         tb = table_of(E, smem_tab);
-                        lc = lens_consts(E, m);
+                        r_last = tb.t[tb.n - 1].x;
+                        lc = lens_consts<CONTRACT>(E, m);
                         have = true;
                     }
                 }
@@ -258,17 +264,18 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
         // ---- advance every busy lane: up to LENS_BURST RK steps, or one aperture ----
         int fate = -1;
         if (have) {
-            CountRows rec;
+            CountRowsT<CONTRACT> rec;
             if (step >= 0) {
 #pragma unroll 1
                 for (int b = 0; b < LENS_BURST; ++b) {
                     int oob = 0;
-                    lens_step(tb, lc, r6, m, P.g, oob, reference_math);
+                    if (CONTRACT) lens_step_contracted(tb, r_last, lc, m, P.g, oob);
+                    else lens_step(tb, lc, r6, m, P.g, oob, reference_math);
                     oob_total += oob & 0xffff;
                     ref_total += oob >> 16;
                     ++steps_total;
                     ++step;
-                    if (outside_radius(m, bore_T)) { fate = P.el[e].fate2; break; }   // "Inside lens"
+                    if (outside_radius<CONTRACT>(m, bore_T)) { fate = P.el[e].fate2; break; }   // "Inside lens"
                     if (step >= n_steps) {
                         lens_exit(P.el[e], m, P.g, rec);
                         step = -1;
@@ -282,11 +289,12 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
                 const DevElement &E = P.el[e];
                 if (E.type == CMT_LENS) {
                     to_plane(m, E.z0, P.g, rec);
-                    if (outside_radius(m, E.p[0])) fate = E.fate;       // "Lens entrance"
+                    if (outside_radius<CONTRACT>(m, E.p[0])) fate = E.fate;       // "Lens entrance"
                     else {
                         step = 0; n_steps = E.n_steps; bore_T = E.p[0];
                         tb = table_of(E, smem_tab);
-                        lc = lens_consts(E, m);
+                        r_last = tb.t[tb.n - 1].x;
+                        lc = lens_consts<CONTRACT>(E, m);
                         if (E.n_steps <= 0) { lens_exit(E, m, P.g, rec); step = -1; ++e; }
                     }
                 } else {
@@ -310,6 +318,7 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
 // ---------------------------------------------------------------------------
 // trajectory kernel: every row of selected molecules
 // ---------------------------------------------------------------------------
+template <bool CONTRACT>
 __global__ void __launch_bounds__(TRAJ_THREADS)
 trajectory_kernel(const __grid_constant__ Params P, int64_t n, const double *__restrict__ state, int n_comp,
                   int64_t state_ld, const int64_t *__restrict__ select, int64_t select_base,
@@ -326,13 +335,13 @@ trajectory_kernel(const __grid_constant__ Params P, int64_t n, const double *__r
     Mol m;
     m.x = state[0 * state_ld + col]; m.y = state[1 * state_ld + col]; m.z = state[2 * state_ld + col];
     m.vx = state[3 * state_ld + col]; m.vy = state[4 * state_ld + col]; m.vz = state[5 * state_ld + col];
-    mol_begin(m, P.g);
+    mol_begin<CONTRACT>(m, P.g);
     if (n_comp >= 10) {
         // resume from an arbitrary row (BeamlineElement.propagate_through on a live Molecule)
         m.ax = state[6 * state_ld + col]; m.ay = state[7 * state_ld + col];
         m.t = state[9 * state_ld + col];
     }
-    WriteRows rec;
+    WriteRowsT<CONTRACT> rec;
     // rows == nullptr: count only; row_offset: compact layout (molecule j starts at row row_offset[j])
     rec.base = rows == nullptr ? nullptr
                : rows + (size_t)(row_offset ? row_offset[j] : j * (int64_t)max_rows) * CMT_ROW_DOUBLES;

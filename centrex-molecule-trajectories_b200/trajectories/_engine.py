@@ -120,10 +120,13 @@ def flatten(elements: Sequence) -> FlatBeamline:
 class DeviceBeamline:
     """Owns a cmt_beamline_t on one GPU."""
 
-    def __init__(self, flat: FlatBeamline, device: int):
+    def __init__(self, flat: FlatBeamline, device: int, math: str = "exact"):
         lib = nat.lib()
         self.flat = flat
         self.device = int(device)
+        if math not in nat.MATH_MODES:
+            raise ValueError(f"math must be one of {sorted(nat.MATH_MODES)}, got {math!r}")
+        self.math = math
         arr = (nat.Element * max(len(flat.elements), 1))(*flat.elements)
         tabs = (nat.Table * max(len(flat.tables), 1))()
         for k, (r, a) in enumerate(flat.tables):
@@ -134,6 +137,7 @@ class DeviceBeamline:
         nat.check(lib.cmt_beamline_create(arr, len(flat.elements), tabs, len(flat.tables), len(flat.fate_names),
                                           flat.fate_detected, G, self.device, C.byref(handle)))
         self.handle = handle
+        nat.check(lib.cmt_beamline_set_math(handle, nat.MATH_MODES[math]))
         self.max_rows = lib.cmt_beamline_max_rows(handle)
 
     def workspace_bytes(self, n: int) -> int:
@@ -148,16 +152,16 @@ class DeviceBeamline:
             pass
 
 
-_handles: Dict[Tuple[bytes, int], DeviceBeamline] = {}
+_handles: Dict[Tuple[bytes, int, str], DeviceBeamline] = {}
 
 
-def device_beamline(flat: FlatBeamline, device: int) -> DeviceBeamline:
-    k = (flat.key, int(device))
+def device_beamline(flat: FlatBeamline, device: int, math: str = "exact") -> DeviceBeamline:
+    k = (flat.key, int(device), math)
     h = _handles.get(k)
     if h is None:
         if len(_handles) > 64:
             _handles.clear()
-        h = _handles[k] = DeviceBeamline(flat, device)
+        h = _handles[k] = DeviceBeamline(flat, device, math)
     return h
 
 
@@ -235,10 +239,11 @@ class Propagator:
     runs beside the walk kernel of chunk i+1.  `join()` makes the current stream wait for them.
     """
 
-    def __init__(self, elements_or_flat, device=None, n_slots: int = 3):
+    def __init__(self, elements_or_flat, device=None, n_slots: int = 3, math: str = "exact"):
         self.flat = elements_or_flat if isinstance(elements_or_flat, FlatBeamline) else flatten(elements_or_flat)
         self.device = resolve_device(device)
-        self.dev = device_beamline(self.flat, self.device)
+        self.math = math
+        self.dev = device_beamline(self.flat, self.device, math)
         torch = _torch()
         self.tdev = torch.device("cuda", self.device)
         self.counters = torch.zeros(len(self.flat.fate_names), dtype=torch.int64, device=self.tdev)

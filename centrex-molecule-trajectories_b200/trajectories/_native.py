@@ -20,6 +20,8 @@ CMT_MAX_TABLES = 8
 CMT_ROW_DOUBLES = 10
 CIRCULAR, RECTANGULAR, FIELDPLATES, LENS = 0, 1, 2, 3
 POS_DISC, POS_GAUSS = 0, 1
+MATH_EXACT, MATH_CONTRACTED = 0, 1
+MATH_MODES = {"exact": MATH_EXACT, "contracted": MATH_CONTRACTED}
 
 
 class Element(C.Structure):
@@ -65,6 +67,7 @@ _SIGNATURES = {
     "cmt_beamline_create": (C.c_int, [C.POINTER(Element), C.c_int, C.POINTER(Table), C.c_int, C.c_int,
                                       C.c_int, C.c_double, C.c_int, C.POINTER(C.c_void_p)]),
     "cmt_beamline_destroy": (None, [C.c_void_p]),
+    "cmt_beamline_set_math": (C.c_int, [C.c_void_p, C.c_int]),
     "cmt_beamline_max_rows": (C.c_int, [C.c_void_p]),
     "cmt_beamline_device": (C.c_int, [C.c_void_p]),
     "cmt_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),

@@ -53,6 +53,11 @@ extern "C" {
 #define CMT_ENOMEM (-3)          /* workspace too small / allocation failed */
 #define CMT_ENODEV (-4)          /* no usable sm_100 device */
 
+/* arithmetic modes (cmt_beamline_set_math) */
+#define CMT_MATH_EXACT 0         /* default: every operation rounds as in the reference, results bit-identical */
+#define CMT_MATH_CONTRACTED 1    /* same algorithm, fused multiply-adds and reciprocal multiplications:
+                                  * ~1e-13 relative agreement, about twice the lens-integrator throughput */
+
 /* element kinds */
 #define CMT_CIRCULAR 0           /* CircularAperture,    apertures.py:83-115  */
 #define CMT_RECTANGULAR 1        /* RectangularAperture, apertures.py:147-189 */
@@ -128,6 +133,10 @@ int cmt_beamline_create(const cmt_element_t *elements, int n_elements,
                         int n_fates, int fate_detected, double g, int device,
                         cmt_beamline_t **out);
 void cmt_beamline_destroy(cmt_beamline_t *bl);
+
+/* Select the arithmetic mode of later launches on this handle (CMT_MATH_*).  Not to be called while
+ * launches on the handle are being issued from another thread. */
+int cmt_beamline_set_math(cmt_beamline_t *bl, int mode);
 
 /* Rows a full trajectory can have: 1 + sum(N_steps) (molecule.py:115-131 without its 10 spare rows). */
 int cmt_beamline_max_rows(const cmt_beamline_t *bl);
