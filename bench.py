@@ -275,11 +275,11 @@ def run_ours(args):
     for k in range(warm):
         step(slots[k % len(slots)])
     prop.join()
-    barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local)          # NVML start-up takes a rank-dependent time: keep it ahead of the barrier
     prop.reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
+    barrier()
     e0.record()
     for k in range(args.steps):
         res = step(slots[k])
