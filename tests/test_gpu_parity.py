@@ -732,3 +732,32 @@ def test_contracted_math_mode(torch_cuda, golden_dir):
     exact = TrajectorySimulator(seed=3)
     exact.run_simulation(bl, "r", N_traj=2_000_000, n_jobs=10)
     assert sum(abs(exact.counter.counter_dict[k] - c.get(k, 0)) for k in exact.counter.counter_dict) <= 4
+
+
+def test_radius_threshold_is_exact(torch_cuda):
+    """`sqrt(x^2+y^2) > d/2` is evaluated on the GPU as `x^2+y^2 > T` with a precomputed T: the two
+    must agree for every double, in particular within a few ulp of the edge."""
+    from trajectories.beamline import Beamline
+    from trajectories.beamline_elements.apertures import CircularAperture
+
+    rng = np.random.default_rng(99)
+    hits = total = 0
+    for trial in range(40):
+        d = float(rng.uniform(1e-4, 0.3)) if trial % 4 else float(2.0 ** rng.integers(-12, -1))
+        R = d / 2
+        bl = Beamline([CircularAperture(name="c", z0=0.5, L=0.0, d=d)])
+        n = 4000
+        theta = rng.uniform(0, 2 * np.pi, n)
+        rho = np.full(n, R)
+        for _ in range(int(rng.integers(0, 4))):                 # a few ulp inside / outside
+            rho = np.nextafter(rho, np.where(rng.random(n) < 0.5, 0.0, 1.0))
+        ic = np.zeros((6, n))
+        ic[0], ic[1] = rho * np.cos(theta), rho * np.sin(theta)
+        ic[0, : n // 4], ic[1, : n // 4] = rho[: n // 4], 0.0    # on an axis: x^2 + 0 exactly
+        ic[2], ic[5] = 0.5, 200.0                                # starts on the plane: dt = 0, position unchanged
+        want = oracle.propagate(bl.elements, ic)
+        got = gpu_propagate(torch_cuda, bl, ic)
+        np.testing.assert_array_equal(got["fate"], want["fate"])
+        hits += int(want["counters"][0])
+        total += n
+    assert 0.2 < hits / total < 0.8                              # both outcomes are well represented
