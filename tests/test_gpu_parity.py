@@ -761,3 +761,30 @@ def test_radius_threshold_is_exact(torch_cuda):
         hits += int(want["counters"][0])
         total += n
     assert 0.2 < hits / total < 0.8                              # both outcomes are well represented
+
+
+def test_abi_from_plain_c(torch_cuda):
+    """examples/abi_demo.c drives libcmt_b200.so from C (dlopen, no Python/torch in that process);
+    its Counter equals the Python path's for the same beamline, table, source and seed."""
+    import json
+    import subprocess
+
+    import __graft_entry__ as ge
+    from trajectories import _native
+    from trajectories.beamline_elements.electrostatic_lens import make_interpolator
+    from trajectories.trajectory_simulator import TrajectorySimulator
+
+    demo = ge.build_abi_demo()
+    out = subprocess.run([str(demo), str(_native.LIB_PATH), "2000000", "7"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    got = json.loads(out.stdout)
+    bl = lens_beamline()
+    lens = bl.find_element("ES lens")
+    r = np.array([1.01 * (lens.d / 2) * i / 221 for i in range(222)])
+    lens.a_interp = make_interpolator(r, -2.0e4 * r)
+    sim = TrajectorySimulator(seed=7)
+    sim.run_simulation(bl, "r", N_traj=2_000_000, n_jobs=10)
+    steps = int(sim.last_work[1])
+    want = dict(sim.counter.counter_dict)
+    assert {k: v for k, v in got.items() if v and k != "lens_rk_steps"} == want
+    assert got["lens_rk_steps"] == steps
