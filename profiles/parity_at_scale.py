@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Parity of the CUDA path with the CPU oracle at sizes beyond the test suite (one-off, round 1).
+
+    python profiles/parity_at_scale.py > profiles/r01_parity_at_scale.json
+"""
+import json
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (str(ROOT), str(ROOT / "centrex-molecule-trajectories_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from oracle import oracle  # noqa: E402
+from trajectories import _engine as eng  # noqa: E402
+from trajectories.centrex import apertures_beamline, lens_beamline, lens_table, spa_beamline  # noqa: E402
+from trajectories.distributions import (CeNTREXPositionDistribution, CeNTREXVelocityDistribution,  # noqa: E402
+                                        GaussianPositionDistribution)
+
+
+def compare(label, bl, vdist, xdist, n, seed, math="exact"):
+    threads = oracle.host_cores()
+    src_o = oracle.make_source(vdist, xdist)
+    ic = oracle.draw(src_o, seed, 0, n, n_threads=threads)          # the oracle's own samples, shared by both sides
+    t0 = time.perf_counter()
+    want = oracle.propagate(bl.elements, ic, n_threads=threads)
+    t_cpu = time.perf_counter() - t0
+    prop = eng.Propagator(bl.elements, 0, math=math)
+    prop.reset()
+    res = prop.propagate_ic(torch.from_numpy(ic).cuda(), want_fate=True, want_final=True)
+    torch.cuda.synchronize()
+    fate = res.fate.cpu().numpy()
+    fin = res.final.cpu().numpy()
+    same = fate == want["fate"]
+    rel = np.abs(fin[:, same] - want["fin"][:, same]) / np.maximum(np.abs(want["fin"][:, same]), 1e-9)
+    bit = (fin[:, same].view(np.int64) == want["fin"][:, same].view(np.int64)).mean()
+    out = dict(case=label, math=math, molecules=n, lens_entries=int(want["work"][1] > 0) and int(res.work[3]),
+               rk_steps=int(want["work"][1]), fate_mismatches=int((~same).sum()), max_rel_err=float(rel.max()),
+               bit_identical_fraction=float(bit), counters_equal=bool((res.counters.cpu().numpy() == want["counters"]).all()),
+               oracle_seconds=round(t_cpu, 2), oracle_threads=threads)
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    v, x = CeNTREXVelocityDistribution(), CeNTREXPositionDistribution()
+    lens = lens_beamline(lens_table())
+    compare("lens beamline, standard source", lens, v, x, 50_000_000, 11)
+    compare("lens beamline, collimated source (most molecules enter the lens)", lens,
+            CeNTREXVelocityDistribution(sigmax=3, sigmay=3), x, 4_000_000, 12)
+    compare("apertures-only beamline, standard source", apertures_beamline(), v, x, 50_000_000, 13)
+    compare("SPA beamline, Gaussian position source", spa_beamline(), v, GaussianPositionDistribution(), 50_000_000, 14)
+    compare("lens beamline, standard source", lens, v, x, 50_000_000, 11, math="contracted")
+    compare("lens beamline, collimated source (most molecules enter the lens)", lens,
+            CeNTREXVelocityDistribution(sigmax=3, sigmay=3), x, 4_000_000, 12, math="contracted")
+
+
+if __name__ == "__main__":
+    main()
