@@ -123,7 +123,7 @@ class TrajectorySimulator:
                  math: str = "exact") -> None:
         """math="exact" (default) reproduces the reference bit for bit; math="contracted" runs the same
         algorithm with fused multiply-adds and reciprocal multiplications (agreement to ~1e-13 relative (1e-9 in the worst case, on coordinates that pass near zero),
-        about twice the lens-integrator throughput)."""
+        1.3-1.6x the lens-integrator throughput)."""
         self.counter = Counter()
         self.results = {}
         self.device = device
