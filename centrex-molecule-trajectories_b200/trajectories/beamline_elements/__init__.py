@@ -2,3 +2,4 @@
 from .apertures import *  # noqa: F401,F403
 from .apertures import BeamlineElement  # noqa: F401  (README-level name; the reference forgets to export it)
 from .electrostatic_lens import *  # noqa: F401,F403
+from .meshes import *  # noqa: F401,F403

@@ -133,6 +133,19 @@ def test_flatten_rejects_unknown_elements():
         eng.flatten([Custom(name="c", z0=0, L=1)])
 
 
+def test_honeycomb_is_importable_but_not_simulated():
+    from trajectories import _engine as eng
+    from trajectories.beamline_elements import Honeycomb
+    from trajectories.molecule import Molecule
+
+    h = Honeycomb(name="mesh", z0=0.3, L=0.01)
+    assert (h.x1, h.x2, h.N_steps()) == (-0.0254, 0.0254, 2)
+    with pytest.raises(TypeError, match="no CUDA implementation"):
+        eng.flatten([h])
+    with pytest.raises(NotImplementedError):
+        h.propagate_through(Molecule())
+
+
 def test_duplicate_names_share_a_fate():
     from trajectories import _engine as eng
     from trajectories.beamline_elements.apertures import CircularAperture
