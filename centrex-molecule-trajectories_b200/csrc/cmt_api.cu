@@ -624,9 +624,10 @@ extern "C" int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t 
     DeviceGuard guard(bl->device);
     CUDA_TRY(guard.status);
     HostPipe &p = g_pipe;
-    // one launch pair per 2^24 molecules: splitting a run further was measured slower (the lens
-    // integrator of a small chunk cannot fill the chip); consecutive chunks alternate streams
-    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 24);
+    // one launch pair per 2^26 molecules (4.3 GB of queue workspace per stream): splitting a run
+    // further was measured slower (the lens integrator of a small chunk cannot keep its lanes
+    // refilled); consecutive chunks alternate streams
+    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 26);
     int rc = pipe_prepare(p, bl, chunk, false, false, false);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(p.d_cnt, 0, (CMT_MAX_FATES + CMT_WORK_SLOTS) * sizeof(int64_t), p.st[0]));
