@@ -788,3 +788,20 @@ def test_abi_from_plain_c(torch_cuda):
     want = dict(sim.counter.counter_dict)
     assert {k: v for k, v in got.items() if v and k != "lens_rk_steps"} == want
     assert got["lens_rk_steps"] == steps
+
+
+def test_run_size_arithmetic_of_the_reference(torch_cuda):
+    """trajectory_simulator.py:48-49: N = int(N_traj / (100 n_jobs)) per loop, remainder dropped;
+    N_traj below 100 n_jobs simulates nothing; unknown apertures of interest never match."""
+    from trajectories.trajectory_simulator import TrajectorySimulator
+
+    bl = apertures_beamline()
+    sim = TrajectorySimulator(seed=1)
+    sim.run_simulation(bl, "small", N_traj=999, n_jobs=10)              # N_loops = 1000 > N_traj
+    assert sim.counter.counter_dict == {} and sim.result.molecules == [] and sim.counter.calculate_efficiency() == 0
+    sim.run_simulation(bl, "odd", N_traj=12_345, n_jobs=3, apertures_of_interest=["no such element"])
+    assert sum(sim.counter.counter_dict.values()) == 300 * 41          # int(12345 / 300) = 41 per loop
+    assert sim.result.molecules == []
+    assert set(sim.results) == {"small", "odd"} and sim.results["odd"].counter is sim.counter
+    sim.run_simulation(bl, "float", N_traj=1e4, n_jobs=1)               # scripts pass floats (argparse type=float)
+    assert sum(sim.counter.counter_dict.values()) == 10_000
