@@ -130,7 +130,7 @@ static void update_trajectory(orc_mol *m, double dt, double g)
     store_row(m);
 }
 
-static void kill(orc_mol *m, int fate) { m->alive = 0; m->fate = fate; }
+static void mark_dead(orc_mol *m, int fate) { m->alive = 0; m->fate = fate; }
 
 static double rho_of(const double x[3])
 {
@@ -145,7 +145,7 @@ static void circular(const orc_element *e, orc_mol *m, double g)
     for (int k = 0; k < 2; k++) {
         double dt = (zs[k] - m->x[2]) / m->v[2];
         update_trajectory(m, dt, g);
-        if (rho_of(m->x) > e->R) { kill(m, e->fate); return; }
+        if (rho_of(m->x) > e->R) { mark_dead(m, e->fate); return; }
     }
 }
 
@@ -158,7 +158,7 @@ static void rectangular(const orc_element *e, orc_mol *m, double g)
         update_trajectory(m, dt, g);
         int inside = (e->x1 < m->x[0] && m->x[0] < e->x2) &&
                      (e->y1 < m->x[1] && m->x[1] < e->y2);
-        if (!inside) { kill(m, e->fate); return; }
+        if (!inside) { mark_dead(m, e->fate); return; }
     }
 }
 
@@ -167,7 +167,7 @@ static void fieldplates(const orc_element *e, orc_mol *m, double g)
 {
     double dt = (e->z0 - m->x[2]) / m->v[2];
     update_trajectory(m, dt, g);
-    if (!(e->x1 < m->x[0] && m->x[0] < e->x2)) { kill(m, e->fate); return; }
+    if (!(e->x1 < m->x[0] && m->x[0] < e->x2)) { mark_dead(m, e->fate); return; }
 
     dt = (e->z1 - m->x[2]) / m->v[2];
     double xn[3];
@@ -176,7 +176,7 @@ static void fieldplates(const orc_element *e, orc_mol *m, double g)
         if (m->v[0] < 0) dt = (e->x1 - m->x[0]) / m->v[0];
         else if (m->v[0] > 0) dt = (e->x2 - m->x[0]) / m->v[0];
         update_trajectory(m, dt, g);
-        kill(m, e->fate);
+        mark_dead(m, e->fate);
         return;
     }
     update_trajectory(m, dt, g);
@@ -234,7 +234,7 @@ static void lens(const orc_beamline *b, const orc_element *e, orc_mol *m)
 {
     double dt = (e->z0 - m->x[2]) / m->v[2];
     update_trajectory(m, dt, b->g);
-    if (rho_of(m->x) > e->R) { kill(m, e->fate); return; }
+    if (rho_of(m->x) > e->R) { mark_dead(m, e->fate); return; }
 
     const int N = e->n_steps;
     dt = e->dz / m->v[2];
@@ -264,7 +264,7 @@ static void lens(const orc_beamline *b, const orc_element *e, orc_mol *m)
         m->steps++;
         store_row(m);
 
-        if (rho_of(m->x) > e->R) { kill(m, e->fate2); return; }
+        if (rho_of(m->x) > e->R) { mark_dead(m, e->fate2); return; }
     }
 
     /* exit step uses the last stored a (= l1 of the final RK step), molecule.py:46-50 */
