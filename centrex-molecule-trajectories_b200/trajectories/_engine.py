@@ -378,7 +378,8 @@ class Propagator:
         with torch.cuda.device(self.device), torch.cuda.graph(graph, stream=st):
             nat.check(nat.lib().cmt_propagate_ic(self.dev.handle, n, int(first_index), ic.data_ptr(), ic.stride(0),
                                                  C.byref(O), ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
-        return GraphedStep(graph, st, fate, (ic, ws, O))
+        # the graph holds raw pointers: keep inputs, workspace, outputs and the beamline handle alive with it
+        return GraphedStep(graph, st, fate, (ic, ws, O, self.dev, self.counters, self.work))
 
     def draw(self, source: nat.Source, seed: int, first_index: int = 0, n: int = 0, index=None):
         """Materialise source samples as a device tensor [6, n]."""
