@@ -403,7 +403,7 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
     if (src) S = *src;
 
     const int64_t tiles = (n + WALK_THREADS - 1) / WALK_THREADS;
-    const int grid_walk = (int)std::min<int64_t>(tiles, (int64_t)bl->n_sm * 8);
+    const int grid_walk = (int)std::min<int64_t>(tiles, (int64_t)bl->n_sm * (2048 / WALK_THREADS));
     {
         ScopedTimer tm(0, st);
         const bool contract = bl->math == CMT_MATH_CONTRACTED;
