@@ -256,6 +256,8 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
             cudaFuncSetAttribute(lens_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
             cudaFuncSetAttribute(trajectory_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
             cudaFuncSetAttribute(trajectory_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            cudaFuncSetAttribute(crossing_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            cudaFuncSetAttribute(crossing_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
         }
     }
     *out = bl;
@@ -493,6 +495,44 @@ extern "C" int cmt_trajectories(const cmt_beamline_t *bl, int64_t n, const doubl
         else
             trajectory_kernel<false><<<grid, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, n, state, n_comp, state_ld, select,
                                                                                 select_base, rows, max_rows, row_offset, n_rows, fate);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return CMT_OK;
+}
+
+extern "C" int cmt_plane_crossings(const cmt_beamline_t *bl, int64_t n, const double *state, int n_comp,
+                                   int64_t state_ld, const int64_t *select, int64_t select_base,
+                                   const double *z_planes, int32_t n_planes, double *out, int64_t out_ld,
+                                   uint8_t *valid, uint8_t *fate, void *stream)
+{
+    if (!bl) return fail(CMT_EINVAL, "beamline handle is NULL");
+    if (n < 0) return fail(CMT_EINVAL, "n < 0");
+    if (n_planes < 1 || n_planes > CMT_MAX_PLANES) return fail(CMT_EINVAL, "n_planes must be 1..%d", CMT_MAX_PLANES);
+    if (!z_planes) return fail(CMT_EINVAL, "z_planes is NULL");
+    ProbePlanes planes;
+    memset(&planes, 0, sizeof(planes));
+    planes.n = n_planes;
+    for (int q = 0; q < n_planes; ++q) {
+        if (z_planes[q] != z_planes[q]) return fail(CMT_EINVAL, "z_planes[%d] is NaN", q);
+        if (q > 0 && z_planes[q] < z_planes[q - 1]) return fail(CMT_EINVAL, "z_planes must be ascending");
+        planes.z[q] = z_planes[q];
+    }
+    if (n == 0) return CMT_OK;
+    if (!state || !out || !valid) return fail(CMT_EINVAL, "state, out and valid are required");
+    if (n_comp != 6 && n_comp != 10) return fail(CMT_EINVAL, "n_comp must be 6 or 10");
+    if (out_ld < n) return fail(CMT_EINVAL, "out_ld < n");
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceGuard guard(bl->device);
+    CUDA_TRY(guard.status);
+    const int grid = (int)((n + TRAJ_THREADS - 1) / TRAJ_THREADS);
+    {
+        ScopedTimer tm(2, st);
+        if (bl->math == CMT_MATH_CONTRACTED)
+            crossing_kernel<true><<<grid, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, planes, n, state, n_comp, state_ld, select,
+                                                                             select_base, out, out_ld, valid, fate);
+        else
+            crossing_kernel<false><<<grid, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, planes, n, state, n_comp, state_ld, select,
+                                                                              select_base, out, out_ld, valid, fate);
     }
     CUDA_TRY(cudaGetLastError());
     return CMT_OK;

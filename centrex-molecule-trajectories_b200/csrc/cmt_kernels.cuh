@@ -360,6 +360,45 @@ trajectory_kernel(const __grid_constant__ Params P, int64_t n, const double *__r
 }
 
 // ---------------------------------------------------------------------------
+// plane-crossing kernel: selected molecules re-propagated with the probe sink
+// ---------------------------------------------------------------------------
+template <bool CONTRACT>
+__global__ void __launch_bounds__(TRAJ_THREADS)
+crossing_kernel(const __grid_constant__ Params P, const __grid_constant__ ProbePlanes planes, int64_t n,
+                const double *__restrict__ state, int n_comp, int64_t state_ld,
+                const int64_t *__restrict__ select, int64_t select_base, double *__restrict__ out, int64_t out_ld,
+                uint8_t *__restrict__ valid, uint8_t *__restrict__ fate_out)
+{
+    extern __shared__ double4 smem_tab[];
+    for (int i = threadIdx.x; i < P.tab_total; i += blockDim.x) smem_tab[i] = P.tab[i];
+    __syncthreads();
+
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int64_t col = select ? select[j] - select_base : j;
+    Mol m;
+    m.x = state[0 * state_ld + col]; m.y = state[1 * state_ld + col]; m.z = state[2 * state_ld + col];
+    m.vx = state[3 * state_ld + col]; m.vy = state[4 * state_ld + col]; m.vz = state[5 * state_ld + col];
+    mol_begin<CONTRACT>(m, P.g);
+    if (n_comp >= 10) {
+        m.ax = state[6 * state_ld + col]; m.ay = state[7 * state_ld + col];
+        m.t = state[9 * state_ld + col];
+    }
+    ProbeRowsT<CONTRACT> rec(planes, out, valid, out_ld, j);
+    rec.row(m);
+
+    int fate = -1, steps = 0, oob = 0;
+    for (int e = 0; e < P.n_el && fate < 0; ++e) {
+        const DevElement &E = P.el[e];
+        if (E.type == CMT_LENS) fate = do_lens(P, E, smem_tab, m, rec, steps, oob);
+        else fate = do_aperture(E, m, P.g, rec);
+    }
+    rec.finish();
+    if (fate < 0) fate = P.fate_detected;
+    if (fate_out) fate_out[j] = (uint8_t)fate;
+}
+
+// ---------------------------------------------------------------------------
 // source only
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

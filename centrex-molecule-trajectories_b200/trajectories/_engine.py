@@ -400,6 +400,45 @@ class Propagator:
                 self.dev.handle, m, state.data_ptr(), n_comp, state.stride(0), sel, int(select_base), rows_ptr,
                 self.dev.max_rows, row_offset_ptr, n_rows.data_ptr(), fate.data_ptr(), _stream_ptr(self.device)))
 
+    def plane_crossings(self, state, z_planes, select=None, select_base=0):
+        """State of the molecules in `state` ([6|10, m] device tensor, optionally gathered through `select`)
+        where they cross the planes `z_planes`: the device form of post_processing.find_radial_pos_dist /
+        find_vel_dist, with no trajectory stored anywhere.
+
+        Returns device tensors (out [n_planes, 5, k] = x, y, vx, vy, vz; valid [n_planes, k] bool;
+        fate [k] uint8), planes in the caller's order."""
+        torch = _torch()
+        zs = np.atleast_1d(np.asarray(z_planes, dtype=np.float64))
+        if zs.ndim != 1 or zs.size == 0:
+            raise ValueError("z_planes must be a non-empty 1-d sequence")
+        if np.isnan(zs).any():
+            raise ValueError("z_planes contains NaN")
+        n_comp = state.shape[0]
+        k_total = select.numel() if select is not None else state.shape[1]
+        assert state.dtype == torch.float64 and (state.stride(1) == 1 or state.shape[1] == 0)
+        out = torch.zeros((zs.size, 5, k_total), dtype=torch.float64, device=self.tdev)
+        valid = torch.zeros((zs.size, k_total), dtype=torch.uint8, device=self.tdev)
+        fate = torch.empty(k_total, dtype=torch.uint8, device=self.tdev)
+        if k_total == 0:
+            return out, valid.bool(), fate
+        order = np.argsort(zs, kind="stable")
+        sel_ptr = select.data_ptr() if select is not None else None
+        with torch.cuda.device(self.device):
+            for lo in range(0, zs.size, nat.CMT_MAX_PLANES):
+                idx = order[lo:lo + nat.CMT_MAX_PLANES]
+                group = np.ascontiguousarray(zs[idx])
+                # sorted planes are written to a contiguous scratch block, then scattered to the caller's order
+                o = torch.zeros((idx.size, 5, k_total), dtype=torch.float64, device=self.tdev)
+                v = torch.zeros((idx.size, k_total), dtype=torch.uint8, device=self.tdev)
+                nat.check(nat.lib().cmt_plane_crossings(
+                    self.dev.handle, k_total, state.data_ptr(), n_comp, state.stride(0), sel_ptr, int(select_base),
+                    group.ctypes.data_as(C.POINTER(C.c_double)), int(idx.size), o.data_ptr(), k_total,
+                    v.data_ptr(), fate.data_ptr(), _stream_ptr(self.device)))
+                where = torch.from_numpy(idx.astype(np.int64)).to(self.tdev)
+                out[where] = o
+                valid[where] = v
+        return out, valid.bool(), fate
+
     def trajectories(self, state, select=None, select_base=0):
         """Full trajectories of the molecules in `state` ([6|10, m] device tensor), optionally gathered
         through `select` (global indices, device int64).

@@ -18,6 +18,7 @@ CMT_MAX_ELEMENTS = 40
 CMT_MAX_FATES = 64
 CMT_MAX_TABLES = 8
 CMT_ROW_DOUBLES = 10
+CMT_MAX_PLANES = 16
 CIRCULAR, RECTANGULAR, FIELDPLATES, LENS = 0, 1, 2, 3
 POS_DISC, POS_GAUSS = 0, 1
 MATH_EXACT, MATH_CONTRACTED = 0, 1
@@ -80,6 +81,9 @@ _SIGNATURES = {
     "cmt_trajectories": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
                                    C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
+    "cmt_plane_crossings": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
+                                      C.c_int64, C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "cmt_run_host_ic": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
     "cmt_run_host_philox": (C.c_int, [C.c_void_p, C.POINTER(Source), C.c_uint64, C.c_int64, C.c_int64,

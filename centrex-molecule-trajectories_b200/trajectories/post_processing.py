@@ -5,6 +5,9 @@ molecule that reached z, take the last stored row before the plane and fly
 ballistically with that row's acceleration (or return the stored row when z is
 one of its rows).  Same results and shapes as the reference; one shared helper
 instead of two copies of the loop.
+
+The same quantities without any stored trajectory (evaluated inside the
+propagation kernel, 40 B per molecule and plane): `TrajectorySimulator.plane_distributions`.
 """
 from __future__ import annotations
 

@@ -230,6 +230,98 @@ class TrajectorySimulator:
     # the reference's README calls the parallel entry point by this name (README.md:52)
     run_simulation_parallel = run_simulation
 
+    def plane_distributions(
+        self,
+        beamline: Beamline,
+        z,
+        elements: Optional[List[str]] = None,
+        vdist=CeNTREXVelocityDistribution(),
+        xdist=CeNTREXPositionDistribution(),
+        N_traj: int = 1000,
+        n_jobs=1,
+        seed: Optional[int] = None,
+    ):
+        """Positions and velocities at the plane(s) `z` without storing any trajectory.
+
+        Same molecules and same numbers as `run_simulation(..., apertures_of_interest=elements)` followed by
+        `post_processing.find_radial_pos_dist(result, z, elements)` / `find_vel_dist` (reference
+        post_processing.py:20-140), but the crossing is evaluated inside the propagation kernel, so memory
+        is 40 B per molecule and plane instead of up to 49 kB per saved trajectory.  `elements=None` keeps
+        every molecule that reaches the plane.  Returns `(xy [m, 2], v [m, 3])` for a scalar `z`, a list
+        of such pairs for a sequence; molecules in global-index order (this rank's block under
+        torch.distributed).  Also updates `.counter` like a run would.
+        """
+        torch = eng._torch()
+        scalar = np.ndim(z) == 0
+        zs = np.atleast_1d(np.asarray(z, dtype=np.float64))
+        N_loops = 100 * n_jobs
+        N = int(N_traj / N_loops)
+        total = N * N_loops
+        flat = eng.flatten(beamline.elements)
+        prop = eng.Propagator(flat, self.device, math=self.math)
+        prop.reset()
+        mask = flat.save_mask(list(elements)) if elements is not None else None
+        rank, world = eng.dist_info()
+        source = eng.make_source(vdist, xdist)
+        chunk = min(self.chunk, 1 << 24)
+        xy = [[] for _ in zs]
+        vel = [[] for _ in zs]
+
+        def probe(ic, select=None):
+            out, valid, fate = prop.plane_crossings(ic, zs, select=select)
+            if mask is None:     # every molecule goes through the crossing kernel: its fates are the Counter
+                prop.counters[: len(flat.fate_names)] += torch.bincount(fate.long(), minlength=len(flat.fate_names))
+            for p in range(len(zs)):
+                cols = out[p][:, valid[p]].cpu().numpy()
+                xy[p].append(cols[0:2].T)
+                vel[p].append(cols[2:5].T)
+
+        if source is not None:
+            if seed is None:
+                seed = self.seed
+            if seed is None:
+                seed = int(np.random.randint(0, 2**62))
+                if world > 1:
+                    s = torch.tensor([seed], dtype=torch.int64, device=prop.tdev if torch.distributed.get_backend() == "nccl" else "cpu")
+                    torch.distributed.broadcast(s, 0)
+                    seed = int(s.item())
+            lo, hi = eng.shard_range(total, rank, world)
+            for first in range(lo, hi, chunk):
+                n = min(chunk, hi - first)
+                if mask is None:
+                    probe(prop.draw(source, seed, first, n))
+                elif mask:
+                    res = prop.propagate_philox(source, seed, first, n, save_mask=mask)
+                    if res.saved_index.numel():
+                        probe(prop.draw(source, seed, index=res.saved_index))
+                else:
+                    prop.propagate_philox(source, seed, first, n)
+        else:
+            for _ in range(rank, N_loops, world):
+                if N == 0:
+                    break
+                vs = np.asarray(vdist.draw(N), dtype=np.float64)   # velocities first, :57-58
+                xs = np.asarray(xdist.draw(N), dtype=np.float64)
+                ic = torch.from_numpy(np.ascontiguousarray(np.concatenate([xs, vs]), dtype=np.float64)).to(prop.tdev)
+                if mask is None:
+                    probe(ic)
+                elif mask:
+                    res = prop.propagate_ic(ic, want_fate=False, save_mask=mask)
+                    if res.saved_index.numel():
+                        probe(ic, select=res.saved_index)
+                else:
+                    prop.propagate_ic(ic, want_fate=False)
+        prop.join()
+
+        counts = eng.allreduce_counts(prop.counters.clone()).cpu().numpy()
+        self.counter = Counter()
+        for name, c in zip(flat.fate_names, counts):
+            if c > 0:
+                self.counter.increment_counter(name, int(c))
+        pairs = [(np.concatenate(a) if a else np.empty((0, 2)), np.concatenate(b) if b else np.empty((0, 3)))
+                 for a, b in zip(xy, vel)]
+        return pairs[0] if scalar else pairs
+
     # -- helpers ----------------------------------------------------------------
     @staticmethod
     def _collect(prop: "eng.Propagator", ic, select=None) -> List[Molecule]:

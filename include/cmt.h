@@ -43,6 +43,7 @@ extern "C" {
 #define CMT_MAX_ELEMENTS 40      /* element table lives in kernel-parameter constant memory */
 #define CMT_MAX_FATES 64         /* fates are stored as uint8 and selected by a 64-bit mask */
 #define CMT_MAX_TABLES 8
+#define CMT_MAX_PLANES 16      /* probe planes per cmt_plane_crossings call */
 #define CMT_WORK_SLOTS 8         /* length of the work-counter array */
 #define CMT_ROW_DOUBLES 10       /* x,y,z,vx,vy,vz,ax,ay,az,t: one Trajectory row (molecule.py:133-144) */
 
@@ -181,6 +182,22 @@ int cmt_trajectories(const cmt_beamline_t *bl, int64_t n, const double *state, i
                      int64_t state_ld, const int64_t *select, int64_t select_base,
                      double *rows, int32_t max_rows, const int64_t *row_offset, int32_t *n_rows,
                      uint8_t *fate, void *stream);
+
+/* State of n selected molecules where they cross given z planes, without
+ * storing trajectories: the device form of find_radial_pos_dist / find_vel_dist
+ * (post_processing.py:20-140) — last row before the plane flown ballistically
+ * with that row's stored acceleration, or the row itself when it lies on the
+ * plane; a molecule whose last row is before the plane does not count (:43).
+ * state / n_comp / state_ld / select / select_base as in cmt_trajectories.
+ * z_planes: HOST array of n_planes <= CMT_MAX_PLANES values in ascending order.
+ * out:   device [n_planes][5][out_ld] (x, y, vx, vy, vz of molecule j in column j);
+ * valid: device [n_planes][out_ld], 1 where the molecule reached the plane
+ *        (columns of out with valid == 0 are left untouched);
+ * fate:  device [n] or NULL. */
+int cmt_plane_crossings(const cmt_beamline_t *bl, int64_t n, const double *state, int n_comp,
+                        int64_t state_ld, const int64_t *select, int64_t select_base,
+                        const double *z_planes, int32_t n_planes, double *out, int64_t out_ld,
+                        uint8_t *valid, uint8_t *fate, void *stream);
 
 /* ---- host-buffer convenience (what a non-CUDA host language binds) ------ */
 

@@ -208,12 +208,52 @@ class Replay(Distribution):
         pass
 
 
+def plane_fixture(table, meta):
+    """post_processing.find_radial_pos_dist / find_vel_dist (post_processing.py:20-140) on reference molecules."""
+    from trajectories.post_processing import find_radial_pos_dist, find_vel_dist
+    from trajectories.trajectory_simulator import Counter, SimulationResult
+
+    xstd = CeNTREXPositionDistribution()
+    ic = draw_reference(321, 400, CeNTREXVelocityDistribution(sigmax=3, sigmay=3), xstd, positions_first=True)
+    ic = np.concatenate([ic, edge_ics(table)], axis=1)
+    bl = lens_beamline(table)
+    names = fate_names(bl)
+    mols, fate = [], []
+    for i in range(ic.shape[1]):
+        m = Molecule()
+        m.init_trajectory(bl, ic[0:3, i].copy(), ic[3:6, i].copy())
+        bl.propagate_through(m)
+        mols.append(m)
+        fate.append(names.index(m.aperture_hit))
+    result = SimulationResult(Counter(), bl, xstd, None, mols)
+    lens = bl.elements[3]
+    # before the source (index -1 quirk), on the source plane, between apertures, on element planes (rows lie on
+    # or within an ulp of them), inside the lens, after it, inside the field plates, past the detection region
+    planes = [0.001, 0.00635, 0.03, bl.elements[0].z0, bl.elements[2].z1, 0.5, lens.z0, 1.2, 1.5, lens.z1, 2.0,
+              2.43, 4.0, 5.43, 6.5]
+    filters = [None, ["Detected"], ["Detected", "Inside lens", "Field plates"]]
+    out = dict(ic=ic, table_r=table[0], table_a=table[1], meta=json.dumps(meta), fate=np.array(fate, dtype=np.int8),
+               fate_names=np.array(names), planes=np.array(planes),
+               filters=np.array(json.dumps(filters)))
+    for p, z in enumerate(planes):
+        for f, elements in enumerate(filters):
+            out[f"xy_{p}_{f}"] = np.asarray(find_radial_pos_dist(result, z, elements), dtype=np.float64)
+            out[f"v_{p}_{f}"] = np.asarray(find_vel_dist(result, z, elements), dtype=np.float64)
+    np.savez_compressed(HERE / "plane_crossings.npz", **out)
+    print("plane crossings:", {float(z): out[f"xy_{p}_0"].shape[0] for p, z in enumerate(planes)}, flush=True)
+
+
 def main():
     t0 = time.time()
     meta = dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0],
                 reference="/root/reference (otimgren/centrex-molecule-trajectories)")
     table = lens_table()
     vstd, xstd = CeNTREXVelocityDistribution(), CeNTREXPositionDistribution()
+
+    # --- post-processing at planes (python make_golden.py planes regenerates only this fixture) ---
+    plane_fixture(table, meta)
+    if sys.argv[1:] == ["planes"]:
+        return
 
     # --- standard distributions, lens beamline + apertures-only beamline (configs 1 and 2) ---
     n_std = 4000

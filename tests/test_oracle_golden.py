@@ -104,3 +104,34 @@ def test_oracle_run_matches_draw_plus_propagate(golden_dir):
     np.testing.assert_array_equal(a["counters"], b["counters"])
     np.testing.assert_array_equal(a["work"], b["work"])
     assert a["counters"].sum() == n
+
+
+def test_plane_crossings_host(golden_dir):
+    """post_processing.find_radial_pos_dist / find_vel_dist (reference post_processing.py:20-140): the package's
+    host implementation on the oracle's rows reproduces what the reference returned, bit for bit — including the
+    index -1 quirk for planes before the source and rows that lie exactly on a plane."""
+    import json
+    from types import SimpleNamespace
+
+    from trajectories.molecule import Molecule
+    from trajectories.post_processing import find_radial_pos_dist, find_vel_dist
+
+    g = np.load(golden_dir / "plane_crossings.npz")
+    bl = lens_beamline((g["table_r"], g["table_a"]))
+    res = oracle.propagate(bl.elements, g["ic"], want_rows=True)
+    np.testing.assert_array_equal(res["fate"], g["fate"])
+    names = res["fate_names"]
+    mols = [Molecule.from_rows(res["rows"][i, : res["n_rows"][i]], names[res["fate"][i]], alive=names[res["fate"][i]] == "Detected")
+            for i in range(g["ic"].shape[1])]
+    result = SimpleNamespace(molecules=mols)
+    filters = json.loads(str(g["filters"]))
+    seen_rows = 0
+    for p, z in enumerate(g["planes"]):
+        for f, elements in enumerate(filters):
+            xy, v = find_radial_pos_dist(result, float(z), elements), find_vel_dist(result, float(z), elements)
+            want_xy, want_v = g[f"xy_{p}_{f}"], g[f"v_{p}_{f}"]
+            assert xy.shape == want_xy.shape and v.shape == want_v.shape, (z, elements)
+            np.testing.assert_array_equal(bits(xy), bits(want_xy))
+            np.testing.assert_array_equal(bits(v), bits(want_v))
+            seen_rows += want_xy.shape[0]
+    assert seen_rows > 5000
