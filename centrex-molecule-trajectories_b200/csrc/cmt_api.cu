@@ -66,6 +66,13 @@ extern "C" int cmt_debug_flags(int flags)
 }
 extern "C" int cmt_version(void) { return CMT_VERSION; }
 
+using LensFn = void (*)(const Params, int64_t, const cmt_outputs_t, Queue);
+static LensFn lens_variant(bool contract, bool mesh)
+{
+    if (contract) return mesh ? lens_kernel<true, true> : lens_kernel<true, false>;
+    return mesh ? lens_kernel<false, true> : lens_kernel<false, false>;
+}
+
 // ---------------------------------------------------------------------------
 // beamline handle
 // ---------------------------------------------------------------------------
@@ -77,6 +84,7 @@ struct cmt_beamline {
     int math;           // CMT_MATH_EXACT / CMT_MATH_CONTRACTED
     double4 *d_tab;     // [tab_total]: (r_j, r_{j+1}, a_j, slope_j)
     size_t tab_bytes;   // dynamic shared memory the lens/trajectory kernels need
+    bool has_mesh;      // a Honeycomb is present: launch the kernel variants that carry its hit test
 };
 
 // Largest double s with sqrt(s) <= R under round-to-nearest, so that the
@@ -151,6 +159,7 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
     bl->max_rows = 1;
     bl->math = CMT_MATH_EXACT;
     bl->d_tab = nullptr;
+    bl->has_mesh = false;
 
     for (int i = 0; i < n_elements; ++i) {
         const cmt_element_t &s = elements[i];
@@ -189,6 +198,17 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
             if (P.first_lens == n_elements) P.first_lens = i;
             break;
         }
+        case CMT_HONEYCOMB:
+            if (s.n_steps < 1 || s.reserved < 1 || (int64_t)s.n_steps * s.reserved > (1 << 30)) {
+                delete bl;
+                return fail(CMT_EINVAL, "element %d: honeycomb needs nx (n_steps) >= 1 and ny (reserved) >= 1", i);
+            }
+            if (!(s.dz > 0.0)) { delete bl; return fail(CMT_EINVAL, "element %d: honeycomb pitch (dz) must be > 0", i); }
+            d.p[0] = s.R; d.p[1] = s.dz; d.p[2] = s.x1; d.p[3] = s.y1;
+            d.tab_len = s.reserved;
+            bl->has_mesh = true;
+            bl->max_rows += 2;
+            break;
         default:
             delete bl;
             return fail(CMT_EINVAL, "element %d: unknown type %d", i, s.type);
@@ -252,8 +272,8 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
         }
         P.tab = bl->d_tab;
         if (bl->tab_bytes > 40 * 1024) {
-            cudaFuncSetAttribute(lens_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
-            cudaFuncSetAttribute(lens_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            for (int v = 0; v < 4; ++v)
+                cudaFuncSetAttribute(lens_variant(v & 1, v >> 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
             cudaFuncSetAttribute(trajectory_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
             cudaFuncSetAttribute(trajectory_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
             cudaFuncSetAttribute(crossing_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
@@ -408,15 +428,17 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
     const int grid_walk = (int)std::min<int64_t>(tiles, (int64_t)bl->n_sm * (2048 / WALK_THREADS));
     {
         ScopedTimer tm(0, st);
+        // variants: source (replay / Philox) x arithmetic (exact / contracted) x Honeycomb test compiled in
+        using WalkFn = void (*)(const Params, const cmt_source_t, uint64_t, const double *, int64_t, int64_t, int64_t,
+                                const cmt_outputs_t, Queue);
+        static const WalkFn walk[2][2][2] = {
+            {{walk_kernel<false, false, false>, walk_kernel<false, false, true>},
+             {walk_kernel<false, true, false>, walk_kernel<false, true, true>}},
+            {{walk_kernel<true, false, false>, walk_kernel<true, false, true>},
+             {walk_kernel<true, true, false>, walk_kernel<true, true, true>}}};
         const bool contract = bl->math == CMT_MATH_CONTRACTED;
-        if (philox && contract)
-            walk_kernel<true, true><<<grid_walk, WALK_THREADS, 0, st>>>(bl->P, S, seed, nullptr, 0, n, first_index, *out, Q);
-        else if (philox)
-            walk_kernel<true, false><<<grid_walk, WALK_THREADS, 0, st>>>(bl->P, S, seed, nullptr, 0, n, first_index, *out, Q);
-        else if (contract)
-            walk_kernel<false, true><<<grid_walk, WALK_THREADS, 0, st>>>(bl->P, S, seed, ic, ic_ld, n, first_index, *out, Q);
-        else
-            walk_kernel<false, false><<<grid_walk, WALK_THREADS, 0, st>>>(bl->P, S, seed, ic, ic_ld, n, first_index, *out, Q);
+        walk[philox][contract][bl->has_mesh]<<<grid_walk, WALK_THREADS, 0, st>>>(
+            bl->P, S, seed, philox ? nullptr : ic, philox ? 0 : ic_ld, n, first_index, *out, Q);
     }
     CUDA_TRY(cudaGetLastError());
     if (has_lens) {
@@ -425,10 +447,8 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
         const int ctas_per_sm = bl->math == CMT_MATH_CONTRACTED ? LENS_MIN_CTAS_CONTRACTED : LENS_MIN_CTAS;
         const int grid_lens = (int)std::min<int64_t>(max_ctas, (int64_t)bl->n_sm * ctas_per_sm);
         ScopedTimer tm(1, st);
-        if (bl->math == CMT_MATH_CONTRACTED)
-            lens_kernel<true><<<grid_lens, LENS_THREADS, bl->tab_bytes, st>>>(bl->P, first_index, *out, Q);
-        else
-            lens_kernel<false><<<grid_lens, LENS_THREADS, bl->tab_bytes, st>>>(bl->P, first_index, *out, Q);
+        lens_variant(bl->math == CMT_MATH_CONTRACTED, bl->has_mesh)<<<grid_lens, LENS_THREADS, bl->tab_bytes, st>>>(
+            bl->P, first_index, *out, Q);
     }
     CUDA_TRY(cudaGetLastError());
     return CMT_OK;

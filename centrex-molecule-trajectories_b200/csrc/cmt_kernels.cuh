@@ -108,7 +108,7 @@ __device__ __forceinline__ void retire(bool done, int fate, const Mol &m, int64_
 // ---------------------------------------------------------------------------
 // walk kernel
 // ---------------------------------------------------------------------------
-template <bool PHILOX, bool CONTRACT>
+template <bool PHILOX, bool CONTRACT, bool MESH>
 __global__ void __launch_bounds__(WALK_THREADS)
 walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source_t S, uint64_t seed,
             const double *__restrict__ ic, int64_t ic_ld, int64_t n, int64_t first_index,
@@ -139,7 +139,7 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
         }
         mol_begin<CONTRACT>(m, P.g);
 
-        CountRowsT<CONTRACT> rec;
+        CountRowsT<CONTRACT, MESH> rec;
         int fate = -1;
         bool to_lens = false;
         if (valid) {
@@ -196,7 +196,7 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
 #ifndef LENS_MIN_CTAS_CONTRACTED
 #define LENS_MIN_CTAS_CONTRACTED 4
 #endif
-template <bool CONTRACT>
+template <bool CONTRACT, bool MESH>
 __global__ void __launch_bounds__(LENS_THREADS, CONTRACT ? LENS_MIN_CTAS_CONTRACTED : LENS_MIN_CTAS)
 lens_kernel(const __grid_constant__ Params P, int64_t first_index,
             const __grid_constant__ cmt_outputs_t O, Queue Q)
@@ -264,7 +264,7 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
         // ---- advance every busy lane: up to LENS_BURST RK steps, or one aperture ----
         int fate = -1;
         if (have) {
-            CountRowsT<CONTRACT> rec;
+            CountRowsT<CONTRACT, MESH> rec;
             if (step >= 0) {
 #pragma unroll 1
                 for (int b = 0; b < LENS_BURST; ++b) {

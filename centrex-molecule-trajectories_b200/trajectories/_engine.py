@@ -64,6 +64,7 @@ def flatten(elements: Sequence) -> FlatBeamline:
     """
     from .beamline_elements.apertures import CircularAperture, FieldPlates, RectangularAperture
     from .beamline_elements.electrostatic_lens import ElectrostaticLens
+    from .beamline_elements.meshes import Honeycomb
 
     if len(elements) > nat.CMT_MAX_ELEMENTS:
         raise ValueError(f"at most {nat.CMT_MAX_ELEMENTS} beamline elements are supported")
@@ -100,10 +101,16 @@ def flatten(elements: Sequence) -> FlatBeamline:
             t.table = len(tables)
             tables.append((np.ascontiguousarray(r, dtype=np.float64), np.ascontiguousarray(a, dtype=np.float64)))
             max_rows += 2 + t.n_steps
+        elif isinstance(e, Honeycomb):
+            t.type, t.fate = nat.HONEYCOMB, fid(e.name)
+            t.R, t.dz = e.polygon_radius, e.pitch
+            t.x1, t.y1 = e.grid_origin()
+            t.n_steps, t.reserved = int(e.nx), int(e.ny)
+            max_rows += 2
         else:
             raise TypeError(
                 f"beamline element {type(e).__name__!r} has no CUDA implementation "
-                "(supported: CircularAperture, RectangularAperture, FieldPlates, ElectrostaticLens)"
+                "(supported: CircularAperture, RectangularAperture, FieldPlates, ElectrostaticLens, Honeycomb)"
             )
         out.append(t)
     fid("Detected")

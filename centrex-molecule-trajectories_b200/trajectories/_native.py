@@ -19,7 +19,7 @@ CMT_MAX_FATES = 64
 CMT_MAX_TABLES = 8
 CMT_ROW_DOUBLES = 10
 CMT_MAX_PLANES = 16
-CIRCULAR, RECTANGULAR, FIELDPLATES, LENS = 0, 1, 2, 3
+CIRCULAR, RECTANGULAR, FIELDPLATES, LENS, HONEYCOMB = 0, 1, 2, 3, 4
 POS_DISC, POS_GAUSS = 0, 1
 MATH_EXACT, MATH_CONTRACTED = 0, 1
 MATH_MODES = {"exact": MATH_EXACT, "contracted": MATH_CONTRACTED}

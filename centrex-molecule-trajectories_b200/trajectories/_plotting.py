@@ -30,6 +30,9 @@ def plot_element(e, axes) -> None:
     elif kind == "FieldPlates":
         axes[0].add_patch(Rectangle((e.z0, e.x2), L, 0.02, color="y"))
         axes[0].add_patch(Rectangle((e.z0, e.x1 - 0.02), L, 0.02, color="y"))
+    elif kind == "Honeycomb":          # meshes.py:126-138
+        axes[0].add_patch(Rectangle((e.z0, e.x1), L, e.x2 - e.x1, color="k"))
+        axes[1].add_patch(Rectangle((e.z0, e.y1), L, e.y2 - e.y1, color="k"))
     elif kind == "ElectrostaticLens":
         for ax in axes[:2]:
             ax.add_patch(Rectangle((e.z0, e.d / 2), L, 0.02, color="b"))

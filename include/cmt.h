@@ -64,6 +64,9 @@ extern "C" {
 #define CMT_RECTANGULAR 1        /* RectangularAperture, apertures.py:147-189 */
 #define CMT_FIELDPLATES 2        /* FieldPlates,         apertures.py:213-270 */
 #define CMT_LENS 3               /* ElectrostaticLens,   electrostatic_lens.py:23-118 */
+#define CMT_HONEYCOMB 4          /* Honeycomb,           meshes.py:26-178 (cell centres as hexalattice.make_grid lays
+                                  * them out, hit test as matplotlib's RegularPolygon.contains_point: both restated,
+                                  * parity unpinned at that third-party boundary) */
 
 /*
  * One flattened beamline element (replaces a BeamlineElement dataclass
@@ -72,17 +75,18 @@ extern "C" {
  * (beamline.py:40-45).
  */
 typedef struct cmt_element {
-    int32_t type;      /* CMT_CIRCULAR .. CMT_LENS */
+    int32_t type;      /* CMT_CIRCULAR .. CMT_HONEYCOMB */
     int32_t fate;      /* fate id recorded on a hit; lens: id of "Lens entrance" */
     int32_t fate2;     /* lens only: id of "Inside lens" */
     int32_t table;     /* lens only: index into the tables given at creation */
-    int32_t n_steps;   /* lens only: int(rint(L/dz)), electrostatic_lens.py:87 */
-    int32_t reserved;
+    int32_t n_steps;   /* lens: int(rint(L/dz)), electrostatic_lens.py:87; honeycomb: nx (cells per row, meshes.py:50) */
+    int32_t reserved;  /* honeycomb: ny (rows, meshes.py:51); 0 otherwise */
     double z0, z1;     /* entrance and exit planes, z1 = z0 + L */
-    double x1, x2;     /* rectangular / field plates: open interval in x */
-    double y1, y2;     /* rectangular: open interval in y */
-    double R;          /* circular aperture / lens bore: d/2 (test is sqrt(x^2+y^2) > R about the origin) */
-    double dz;         /* lens only: integration step along z */
+    double x1, x2;     /* rectangular / field plates: open interval in x; honeycomb: x1 = make_grid's mid_x */
+    double y1, y2;     /* rectangular: open interval in y; honeycomb: y1 = make_grid's mid_y */
+    double R;          /* circular aperture / lens bore: d/2 (test is sqrt(x^2+y^2) > R about the origin);
+                        * honeycomb: polygon radius (cell_wall_length*sqrt(3) - cell_wall_thickness/2)/2, meshes.py:73-77 */
+    double dz;         /* lens: integration step along z; honeycomb: centre pitch cell_wall_length*sqrt(3), meshes.py:58 */
 } cmt_element_t;
 
 /* Lens radial-acceleration table a_r(r): what ElectrostaticLens.a_interp holds

@@ -12,6 +12,7 @@
  *   beamline_elements/apertures.py:157-189 RectangularAperture
  *   beamline_elements/apertures.py:221-270 FieldPlates
  *   beamline_elements/electrostatic_lens.py:48-118,215-228  ElectrostaticLens
+ *   beamline_elements/meshes.py:84-117     Honeycomb.propagate_through (see below)
  *   distributions.py:69-76,112-119,155-162 (distribution shapes; the bit stream
  *                                           is the build's Philox, not NumPy's)
  *   trajectory_simulator.py:62-76          per-molecule loop + Counter
@@ -23,6 +24,14 @@
  * (same numpy 2.3.5 / scipy 1.18.1 / glibc as the container).  The Stark-curve
  * producer (centrex_TlF, external and unpinned) is NOT restated here: the lens
  * acceleration table is an input ("parity unpinned" at that boundary only).
+ *
+ * Honeycomb: the reference's own logic (stepping, nearest-centre argmin, `if not idx`,
+ * fate) is pinned by tests/golden/honeycomb.npz, but its geometry comes from two
+ * third-party packages that are absent here and pinned nowhere by the reference:
+ * hexalattice.make_grid (cell centres) and matplotlib's RegularPolygon.contains_point
+ * (hit test).  Both are restated from their published algorithms -- PARITY UNPINNED at
+ * that boundary: the golden file was produced with the restatements in oracle/stubs
+ * standing in for the real packages.
  *
  * Arithmetic notes that matter for bit parity with the reference as executed:
  *   - `delta_t**2` on a numpy float64 *scalar* goes through libm pow(), which
@@ -45,18 +54,20 @@
 #define ORC_RECTANGULAR 1
 #define ORC_FIELDPLATES 2
 #define ORC_LENS 3
+#define ORC_HONEYCOMB 4
 
 typedef struct {
     int32_t type;     /* ORC_* */
     int32_t fate;     /* fate id on hit; lens: id of "Lens entrance" */
     int32_t fate2;    /* lens: id of "Inside lens" */
     int32_t table;    /* lens: table index */
-    int32_t n_steps;  /* lens: int(rint(L/dz)), electrostatic_lens.py:87 */
-    int32_t pad_;
+    int32_t n_steps;  /* lens: int(rint(L/dz)), electrostatic_lens.py:87; honeycomb: nx */
+    int32_t pad_;     /* honeycomb: ny */
     double z0, z1;
     double x1, x2, y1, y2; /* rectangular / field-plate edges, apertures.py:157-163,221-225 */
-    double R;              /* d/2 for circular aperture and lens bore */
-    double dz;             /* lens step, electrostatic_lens.py:30 */
+    double R;              /* d/2 for circular aperture and lens bore; honeycomb: polygon radius, meshes.py:73-77 */
+    double dz;             /* lens step, electrostatic_lens.py:30; honeycomb: pitch (min_diam), meshes.py:58;
+                              honeycomb also: x1 = mid_x, y1 = mid_y of make_grid */
 } orc_element;
 
 typedef struct {
@@ -272,6 +283,71 @@ static void lens(const orc_beamline *b, const orc_element *e, orc_mol *m)
     update_trajectory(m, dt, b->g);
 }
 
+/* ---- Honeycomb, meshes.py:84-117 ------------------------------------------ */
+/* np.cos / np.sin of 2*pi/6*k + pi/2 (Path.unit_regular_polygon(6)); checked against NumPy by the tests */
+static const double hex_ux[6] = {0x1.1a62633145c07p-54, -0x1.bb67ae8584ca9p-1, -0x1.bb67ae8584cacp-1,
+                                 -0x1.a79394c9e8a0ap-53, 0x1.bb67ae8584ca8p-1, 0x1.bb67ae8584caep-1};
+static const double hex_uy[6] = {0x1.0000000000000p+0, 0x1.0000000000003p-1, -0x1.ffffffffffffbp-2,
+                                 -0x1.0000000000000p+0, -0x1.0000000000004p-1, 0x1.ffffffffffff3p-2};
+#define HEX_RATIO 0x1.bb67ae8584caap-1 /* np.sqrt(3) / 2 */
+
+static void hex_centre(const orc_element *e, long idx, double *xc, double *yc)
+{
+    /* hexalattice.make_grid: row-major, odd rows shifted by half a pitch, middle cell moved to the origin */
+    long row = idx / e->n_steps, col = idx % e->n_steps;
+    double cx = (double)col;
+    if (row & 1) cx += 0.5;
+    *xc = cx * e->dz - e->x1;
+    *yc = ((double)row * HEX_RATIO) * e->dz - e->y1;
+}
+
+static long hex_nearest(const orc_element *e, double px, double py)
+{
+    /* idx = np.argmin(np.sqrt((px - xcoords)**2 + (py - ycoords)**2)), meshes.py:105-109: every centre, first minimum;
+     * a NaN distance wins over everything that follows (np.argmin propagates the first NaN) */
+    long n = (long)e->n_steps * e->pad_, best = 0;
+    double best_rho = 0.0;
+    for (long i = 0; i < n; i++) {
+        double xc, yc;
+        hex_centre(e, i, &xc, &yc);
+        double dx = px - xc, dy = py - yc;
+        double rho = sqrt(dx * dx + dy * dy);
+        if (rho != rho) return i;
+        if (i == 0 || rho < best_rho) { best_rho = rho; best = i; }
+    }
+    return best;
+}
+
+static int hex_contains(const orc_element *e, long idx, double tx, double ty)
+{
+    /* RegularPolygon((xc, yc), 6, radius=R).contains_point((tx, ty)): crossings-multiply test of matplotlib's
+     * _path.h on the vertices unit * R + centre; non-finite points are outside */
+    if (!isfinite(tx) || !isfinite(ty)) return 0;
+    double xc, yc;
+    hex_centre(e, idx, &xc, &yc);
+    int inside = 0;
+    for (int k = 0; k < 6; k++) {
+        int k1 = (k + 1) % 6;
+        double x0 = hex_ux[k] * e->R + xc, y0 = hex_uy[k] * e->R + yc;
+        double x1 = hex_ux[k1] * e->R + xc, y1 = hex_uy[k1] * e->R + yc;
+        int f0 = y0 >= ty, f1 = y1 >= ty;
+        if (f0 != f1 && (((y1 - ty) * (x0 - x1) >= (x1 - tx) * (y0 - y1)) == f1)) inside ^= 1;
+    }
+    return inside;
+}
+
+static void honeycomb(const orc_element *e, orc_mol *m, double g)
+{
+    long idx = 0;                                   /* `idx = None`, and `if not idx` is also true for cell 0 */
+    const double zs[2] = {e->z0, e->z1};
+    for (int k = 0; k < 2; k++) {
+        double dt = (zs[k] - m->x[2]) / m->v[2];
+        update_trajectory(m, dt, g);
+        if (idx == 0) idx = hex_nearest(e, m->x[0], m->x[1]);
+        if (!hex_contains(e, idx, m->x[0], m->x[1])) { mark_dead(m, e->fate); return; }
+    }
+}
+
 static void propagate_one(const orc_beamline *b, orc_mol *m)
 {
     /* Beamline.propagate_through, beamline.py:20-38 */
@@ -282,6 +358,7 @@ static void propagate_one(const orc_beamline *b, orc_mol *m)
         case ORC_RECTANGULAR: rectangular(e, m, b->g); break;
         case ORC_FIELDPLATES: fieldplates(e, m, b->g); break;
         case ORC_LENS:        lens(b, e, m); break;
+        case ORC_HONEYCOMB:   honeycomb(e, m, b->g); break;
         default: break;
         }
         if (!m->alive) break;

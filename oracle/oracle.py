@@ -21,7 +21,7 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "_build" / "libcmt_oracle.so"
 G = 9.80665  # scipy.constants.g, molecule.py:6
 
-CIRCULAR, RECTANGULAR, FIELDPLATES, LENS = 0, 1, 2, 3
+CIRCULAR, RECTANGULAR, FIELDPLATES, LENS, HONEYCOMB = 0, 1, 2, 3, 4
 
 ELEMENT_DTYPE = np.dtype(
     [
@@ -121,6 +121,18 @@ def flatten(elements) -> Flat:
             rs.append(x)
             as_.append(y)
             max_rows += 2 + int(t["n_steps"])
+        elif kind == "Honeycomb":
+            # meshes.py:50-62,73-77 + hexalattice.make_grid's origin (restated, see cmt_oracle.c header)
+            nx = int(np.ceil(e.width / (e.cell_wall_length * np.sqrt(3))))
+            ny = int(np.ceil(e.height / (e.cell_wall_length * 3 / 2)))
+            pitch = e.cell_wall_length * np.sqrt(3)
+            mid_x = (np.ceil(nx / 2) - 1) + 0.5 * (np.ceil(ny / 2) % 2 == 0)
+            mid_y = (np.ceil(ny / 2) - 1) * (np.sqrt(3) / 2)
+            t["type"], t["fate"] = HONEYCOMB, fid(e.name)
+            t["n_steps"], t["pad_"] = nx, ny
+            t["dz"], t["x1"], t["y1"] = pitch, mid_x * pitch, mid_y * pitch
+            t["R"] = (e.cell_wall_length * np.sqrt(3) - e.cell_wall_thickness / 2) / 2
+            max_rows += 2
         else:
             raise TypeError(f"oracle: unsupported beamline element {kind}")
     fid("Detected")

@@ -15,3 +15,14 @@ def standard_ics(n, seed, sigma_perp=39.5):
     ic[0], ic[1], ic[2] = rr * np.cos(th), rr * np.sin(th), 0.25 * 0.0254
     ic[3], ic[4], ic[5] = rng.normal(0, sigma_perp, n), rng.normal(0, sigma_perp, n), rng.normal(184, 16, n)
     return ic
+
+
+def honeycomb_beamline(L=0.05, **mesh_kwargs):
+    """A Honeycomb between two apertures (the beamline of tests/golden/honeycomb.npz)."""
+    from trajectories.beamline import Beamline
+    from trajectories.beamline_elements import CircularAperture, Honeycomb, RectangularAperture
+
+    front = CircularAperture(z0=0.1, L=0.01, d=0.12, name="front")
+    mesh = Honeycomb(z0=0.3, L=L, name="Honeycomb", **mesh_kwargs)
+    back = RectangularAperture(z0=0.6, L=0.01, w=0.06, h=0.06, name="back")
+    return Beamline([front, mesh, back])

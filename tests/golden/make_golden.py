@@ -243,6 +243,59 @@ def plane_fixture(table, meta):
     print("plane crossings:", {float(z): out[f"xy_{p}_0"].shape[0] for p, z in enumerate(planes)}, flush=True)
 
 
+def honeycomb_beamline(L=0.05):
+    """A Honeycomb between two apertures (no example of the reference uses the element; the geometry is its defaults)."""
+    from trajectories.beamline_elements.meshes import Honeycomb
+
+    front = CircularAperture(z0=0.1, L=0.01, d=0.12, name="front")
+    mesh = Honeycomb(z0=0.3, L=L, name="Honeycomb")
+    back = RectangularAperture(z0=0.6, L=0.01, w=0.06, h=0.06, name="back")
+    return Beamline([front, mesh, back])
+
+
+def honeycomb_fixture(meta):
+    """Honeycomb.propagate_through (meshes.py:84-117) executed from the reference source.  hexalattice and
+    matplotlib are absent: oracle/stubs restates make_grid and RegularPolygon.contains_point (PARITY UNPINNED
+    at that third-party boundary; the reference's own logic around them is what this fixture pins)."""
+    import warnings
+
+    warnings.simplefilter("ignore", DeprecationWarning)
+    bl = honeycomb_beamline()
+    mesh = bl.elements[1]
+    rng = np.random.default_rng(2024)
+    n = 3000
+    ic = np.empty((6, n))
+    ic[0], ic[1], ic[2] = rng.uniform(-0.032, 0.032, n), rng.uniform(-0.032, 0.032, n), 0.0
+    ic[3], ic[4], ic[5] = rng.normal(0, 3.0, n), rng.normal(0, 3.0, n), rng.normal(184, 16, n)
+    # molecules aimed at cell 0 (bottom-left corner) that drift towards cell 1 / the row above inside the mesh:
+    # `if not idx` (meshes.py:104) re-assigns the cell at z1 only for them
+    x0c, y0c = float(mesh.xcoords[0, 0]), float(mesh.ycoords[0, 0])
+    pitch = mesh.cell_wall_length * np.sqrt(3)
+    k = 400
+    vz = rng.normal(184, 5, k)
+    tx, ty = x0c + rng.uniform(-0.001, 0.001, k), y0c + rng.uniform(-0.001, 0.001, k)      # position at z0
+    drift = rng.choice([0.0, 1.0], k)[None, :] * np.array([[pitch], [0.0]]) + rng.normal(0, 3e-4, (2, k))
+    vx, vy = drift[0] / (mesh.L / vz), drift[1] / (mesh.L / vz)
+    t0 = mesh.z0 / vz
+    extra = np.array([tx - vx * t0, ty - vy * t0 + 0.5 * 9.80665 * t0 ** 2, np.zeros(k), vx, vy, vz])
+    # exactly on cell centres, on vertices and edge mid-points of a cell (boundary of the hit test)
+    c = 200
+    xc, yc = float(mesh.xcoords[c, 0]), float(mesh.ycoords[c, 0])
+    rad = (mesh.cell_wall_length * np.sqrt(3) - mesh.cell_wall_thickness / 2) / 2
+    th = 2 * np.pi / 6 * np.arange(6) + np.pi / 2
+    pts = [(xc, yc)] + [(xc + rad * np.cos(a), yc + rad * np.sin(a)) for a in th] \
+        + [(xc + rad * np.sqrt(3) / 2 * np.cos(a + np.pi / 6), yc + rad * np.sqrt(3) / 2 * np.sin(a + np.pi / 6)) for a in th]
+    special = np.array([[px, py, mesh.z0, 0.0, 0.0, 184.0] for px, py in pts]).T
+    ic = np.concatenate([ic, extra, special], axis=1)
+    res = run_reference(bl, ic, rows_per_fate=2)
+    np.savez_compressed(HERE / "honeycomb.npz", ic=ic, meta=json.dumps(meta), n_cell0=k,
+                        xcoords=np.asarray(mesh.xcoords), ycoords=np.asarray(mesh.ycoords), nx=mesh.nx, ny=mesh.ny,
+                        **{f"hc_{key}": v for key, v in res.items()})
+    names = list(res["fate_names"])
+    print("honeycomb: fates", dict(zip(names, np.bincount(res["fate"], minlength=len(names)))),
+          "| aimed at cell 0:", dict(zip(names, np.bincount(res["fate"][n:n + k], minlength=len(names)))), flush=True)
+
+
 def main():
     t0 = time.time()
     meta = dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0],
@@ -251,8 +304,14 @@ def main():
     vstd, xstd = CeNTREXVelocityDistribution(), CeNTREXPositionDistribution()
 
     # --- post-processing at planes (python make_golden.py planes regenerates only this fixture) ---
-    plane_fixture(table, meta)
+    if sys.argv[1:] != ["honeycomb"]:
+        plane_fixture(table, meta)
     if sys.argv[1:] == ["planes"]:
+        return
+
+    # --- Honeycomb (python make_golden.py honeycomb regenerates only this fixture) ---
+    honeycomb_fixture(meta)
+    if sys.argv[1:] == ["honeycomb"]:
         return
 
     # --- standard distributions, lens beamline + apertures-only beamline (configs 1 and 2) ---

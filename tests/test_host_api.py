@@ -133,17 +133,45 @@ def test_flatten_rejects_unknown_elements():
         eng.flatten([Custom(name="c", z0=0, L=1)])
 
 
-def test_honeycomb_is_importable_but_not_simulated():
-    from trajectories import _engine as eng
-    from trajectories.beamline_elements import Honeycomb
-    from trajectories.molecule import Molecule
+def test_honeycomb_geometry(golden_dir):
+    """Honeycomb (meshes.py:26-82): derived attributes, the cell grid of hexalattice.make_grid as the oracle's
+    stand-in lays it out (tests/golden/honeycomb.npz stores what the reference's element held), flattening."""
+    import numpy as np
 
+    from oracle import oracle
+    from trajectories import _engine as eng
+    from trajectories import _native as nat
+    from trajectories.beamline_elements import Honeycomb
+
+    g = np.load(golden_dir / "honeycomb.npz")
     h = Honeycomb(name="mesh", z0=0.3, L=0.01)
-    assert (h.x1, h.x2, h.N_steps()) == (-0.0254, 0.0254, 2)
-    with pytest.raises(TypeError, match="no CUDA implementation"):
-        eng.flatten([h])
-    with pytest.raises(NotImplementedError):
-        h.propagate_through(Molecule())
+    assert (h.x1, h.x2, h.y1, h.y2, h.N_steps()) == (-0.0254, 0.0254, -0.0254, 0.0254, 2)
+    assert (h.nx, h.ny) == (int(g["nx"]), int(g["ny"])) == (19, 22)
+    assert h.xcoords.shape == h.ycoords.shape == (19 * 22, 1)
+    np.testing.assert_array_equal(h.xcoords.view(np.int64), g["xcoords"].view(np.int64))     # bit for bit
+    np.testing.assert_array_equal(h.ycoords.view(np.int64), g["ycoords"].view(np.int64))
+    assert np.abs(h.xcoords).min() == 0.0 and np.abs(h.ycoords).min() == 0.0                 # a cell sits on the origin
+    flat = eng.flatten([h])
+    e = flat.elements[0]
+    assert (e.type, e.n_steps, e.reserved) == (nat.HONEYCOMB, 19, 22)
+    o = oracle.flatten([h]).elements[0]                                                       # the oracle derives the same numbers itself
+    assert (e.R, e.dz, e.x1, e.y1) == (o["R"], o["dz"], o["x1"], o["y1"])
+    # centres as the kernels compute them: ((col + row%2/2) * pitch) - mid_x, ((row * sqrt(3)/2) * pitch) - mid_y
+    col, row = np.arange(19 * 22) % 19, np.arange(19 * 22) // 19
+    np.testing.assert_array_equal((col + 0.5 * (row % 2)) * e.dz - e.x1, h.xcoords[:, 0])
+    np.testing.assert_array_equal((row * (np.sqrt(3) / 2)) * e.dz - e.y1, h.ycoords[:, 0])
+    # the unit hexagon hard-coded in csrc/cmt_device.cuh and oracle/cmt_oracle.c is NumPy's
+    theta = (2 * np.pi / 6) * np.arange(7) + np.pi / 2.0
+    want = [float.fromhex(v) for v in ("0x1.1a62633145c07p-54", "-0x1.bb67ae8584ca9p-1", "-0x1.bb67ae8584cacp-1",
+                                       "-0x1.a79394c9e8a0ap-53", "0x1.bb67ae8584ca8p-1", "0x1.bb67ae8584caep-1")]
+    assert list(np.cos(theta)[:6]) == want
+    want = [float.fromhex(v) for v in ("0x1.0000000000000p+0", "0x1.0000000000003p-1", "-0x1.ffffffffffffbp-2",
+                                       "-0x1.0000000000000p+0", "-0x1.0000000000004p-1", "0x1.ffffffffffff3p-2")]
+    assert list(np.sin(theta)[:6]) == want
+    assert float(np.sqrt(3) / 2) == float.fromhex("0x1.bb67ae8584caap-1")
+    for src in ("centrex-molecule-trajectories_b200/csrc/cmt_device.cuh", "oracle/cmt_oracle.c"):
+        text = (golden_dir.parent.parent / src).read_text()
+        assert "0x1.1a62633145c07p-54" in text and "0x1.ffffffffffff3p-2" in text and "0x1.bb67ae8584caap-1" in text
 
 
 def test_duplicate_names_share_a_fate():

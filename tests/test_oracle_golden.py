@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle
-from tests.beamlines import apertures_beamline, lens_beamline, spa_beamline
+from tests.beamlines import apertures_beamline, honeycomb_beamline, lens_beamline, spa_beamline
 
 
 def bits(a):
@@ -49,6 +49,16 @@ def test_spa(golden_dir):
     res = check_case(g, "spa", spa_beamline())
     det = res["fate"] == res["fate_names"].index("Detected")
     assert (res["n_rows"][det] == 19).all()       # 1 + 2 x 9 rows, SURVEY.md 3.4
+
+
+def test_honeycomb(golden_dir):
+    """Honeycomb.propagate_through as the reference executes it (geometry packages restated: parity unpinned there)."""
+    g = np.load(golden_dir / "honeycomb.npz")
+    res = check_case(g, "hc", honeycomb_beamline())
+    names = res["fate_names"]
+    n_cell0 = int(g["n_cell0"])
+    aimed = res["fate"][3000:3000 + n_cell0]
+    assert (aimed == names.index("Detected")).mean() > 0.8      # `if not idx`: cell 0 is re-assigned at z1
 
 
 def test_row_counts(golden_dir):
