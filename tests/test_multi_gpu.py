@@ -29,8 +29,11 @@ def _worker(rank, world, port, out_dir):
     sim = TrajectorySimulator(device=rank, seed=21, chunk=1 << 20)
     sim.run_simulation(lens_beamline(lens_table()), "r", N_traj=3_000_000, apertures_of_interest=["Detected"], n_jobs=10)
     first_rows = np.array([m.trajectory.x[0] for m in sim.result.molecules])
-    np.savez(Path(out_dir) / f"rank{rank}.npz", keys=np.array(list(sim.counter.counter_dict.keys())),
-             vals=np.array(list(sim.counter.counter_dict.values())), saved=first_rows)
+    keys, vals = list(sim.counter.counter_dict.keys()), list(sim.counter.counter_dict.values())
+    # plane probe: same sharding, Counter all-reduced, crossings stay on the owning rank
+    xy, v = sim.plane_distributions(lens_beamline(lens_table()), 2.0, elements=["Detected"], N_traj=3_000_000, n_jobs=10)
+    assert sim.counter.counter_dict == dict(zip(keys, vals))
+    np.savez(Path(out_dir) / f"rank{rank}.npz", keys=np.array(keys), vals=np.array(vals), saved=first_rows, xy=xy, v=v)
     dist.destroy_process_group()
 
 
@@ -58,3 +61,7 @@ def test_two_ranks_equal_one(tmp_path):
     both = np.concatenate([r0["saved"].reshape(-1, 3), r1["saved"].reshape(-1, 3)])
     single = np.array([m.trajectory.x[0] for m in sim.result.molecules])
     np.testing.assert_array_equal(both, single)
+    xy, v = sim.plane_distributions(lens_beamline(lens_table()), 2.0, elements=["Detected"], N_traj=3_000_000, n_jobs=10)
+    np.testing.assert_array_equal(np.concatenate([r0["xy"], r1["xy"]]), xy)
+    np.testing.assert_array_equal(np.concatenate([r0["v"], r1["v"]]), v)
+    assert xy.shape[0] == single.shape[0] > 100
