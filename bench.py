@@ -45,9 +45,9 @@ UNIT = "molecules/s"
 WORKLOAD = ("configs[1]: examples/lens_simulation_beamline.py full CeNTREX beamline with ElectrostaticLens, "
             "J=2 mJ=0 Stark curve at 27.6 kV, CeNTREX velocity/position distributions")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload at
-# 1e7 molecules (profiles/r01_full_d_final.txt); scaled linearly when --molecules differs
+# 1e7 molecules (profiles/r01_full_e_round_end.txt); scaled linearly when --molecules differs
 NCU_TRAFFIC_LENS_1E7 = 3.52e6
-NCU_TRAFFIC_WALK_1E7 = 481.3e6 + 14.7e6
+NCU_TRAFFIC_WALK_1E7 = 481.3e6 + 17.8e6
 # algorithmic work per unit
 FLOP_PER_ROW = 30      # one ballistic step + hit test
 FLOP_PER_STEP = 162    # one lens RK step (4 force evaluations)
@@ -365,8 +365,8 @@ def run_ours(args):
     roofline = {
         "kernel": "lens_kernel", "bound": "fp64", "achieved": lens_tflops, "peak": fp64_peak_tflops,
         "unit": "TFLOP/s", "frac": (lens_tflops / fp64_peak_tflops) if lens_tflops else None,
-        "traffic": NCU_TRAFFIC_LENS_1E7 * n / 1e7, "traffic_source": "profiles/r01_full_d_final.txt (ncu --set full)",
-        "fp64_pipe_utilisation_ncu": 0.644,
+        "traffic": NCU_TRAFFIC_LENS_1E7 * n / 1e7, "traffic_source": "profiles/r01_full_e_round_end.txt (ncu --set full)",
+        "fp64_pipe_utilisation_ncu": 0.650,
         "peak_source": "measured live: cmt_fp64_peak DFMA stream (no FP64 figure in MEASURED_PEAKS.json)",
         "algorithmic_flop_per_launch": flop_lens, "avg_launch_ms": lens_ms,
         "share_of_step": lens_ms / (ms_seq / args.steps) if ms_seq > 0 else None,
@@ -377,7 +377,7 @@ def run_ours(args):
     roofline_walk = {
         "kernel": "walk_kernel<ic>", "bound": "hbm", "achieved": walk_gbs, "peak": hbm_peak, "unit": "GB/s",
         "frac": (walk_gbs / hbm_peak) if walk_gbs else None, "traffic": NCU_TRAFFIC_WALK_1E7 * n / 1e7,
-        "traffic_source": "profiles/r01_full_d_final.txt (ncu --set full)", "peak_source": hbm_src,
+        "traffic_source": "profiles/r01_full_e_round_end.txt (ncu --set full)", "peak_source": hbm_src,
         "algorithmic_bytes_per_launch": BYTES_PER_MOLECULE * n, "avg_launch_ms": walk_ms,
         "share_of_step": walk_ms / (ms_seq / args.steps) if ms_seq > 0 else None,
         "algorithmic_flop_per_launch": flop_rows,
