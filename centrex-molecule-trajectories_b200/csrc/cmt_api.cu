@@ -240,6 +240,59 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
         F.next_element = e;
     }
 
+    // FP32 fate filter: the leading run of circular / rectangular / field-plate elements as
+    // single-precision planes, closed by the first lens' entrance plane when it follows directly.
+    // Built only when every threshold is an ordinary number (the error model of filter_fate
+    // assumes normal single-precision magnitudes); otherwise n = 0 and the walk is binary64 only.
+    {
+        FilterPlanes &F = P.filt;
+        F.n = 0; F.covers_all = 0;
+        F.hg = (float)(0.5 * g);
+        F.g_abs = (float)std::fabs(g);
+        bool usable = std::isfinite(g) && std::fabs(g) < 1e6;
+        const float inf = std::numeric_limits<float>::infinity();
+        auto ordinary = [](double v) { return std::isfinite(v) && std::fabs(v) < 1e15; };
+        auto edge_ok = [](double v) { return !std::isnan(v) && (std::isinf(v) || std::fabs(v) < 1e15); };
+        auto circle = [&](double z, double T, int fate) {
+            if (!(ordinary(z) && std::isfinite(T) && T >= 1e-30 && T <= 1e30)) { usable = false; return; }
+            FilterPlane &pl = F.pl[F.n++];
+            pl.z = (float)z; pl.kind = CMT_FILTER_CIRCLE; pl.fate = fate;
+            pl.a = (float)T; pl.b = pl.c = pl.d = 0.f;
+            pl.tol = std::ldexp(std::fabs(pl.a), -21) + 1e-37f;
+        };
+        auto box = [&](double z, double x1, double x2, double y1, double y2, int fate) {
+            if (!(ordinary(z) && edge_ok(x1) && edge_ok(x2) && edge_ok(y1) && edge_ok(y2))) { usable = false; return; }
+            FilterPlane &pl = F.pl[F.n++];
+            pl.z = (float)z; pl.kind = CMT_FILTER_BOX; pl.fate = fate;
+            pl.a = (float)x1; pl.b = (float)x2; pl.c = (float)y1; pl.d = (float)y2;
+            float m = 0.f;
+            for (float v : {pl.a, pl.b, pl.c, pl.d}) if (std::isfinite(v)) m = std::max(m, std::fabs(v));
+            pl.tol = std::ldexp(m, -21) + 1e-37f;
+        };
+        int e = 0;
+        for (; usable && e < n_elements && F.n + 2 <= CMT_MAX_FILTER_PLANES; ++e) {
+            const DevElement &d = P.el[e];
+            if (d.type == CMT_CIRCULAR) {
+                circle(d.z0, d.p[0], d.fate);
+                if (usable) circle(d.z1, d.p[0], d.fate);
+            } else if (d.type == CMT_RECTANGULAR) {
+                box(d.z0, d.p[0], d.p[1], d.p[2], d.p[3], d.fate);
+                if (usable) box(d.z1, d.p[0], d.p[1], d.p[2], d.p[3], d.fate);
+            } else if (d.type == CMT_FIELDPLATES) {
+                // x only, at z0 and (look-ahead or wall crossing, same fate and one row either way) at z1
+                box(d.z0, d.p[0], d.p[1], -inf, inf, d.fate);
+                if (usable) box(d.z1, d.p[0], d.p[1], -inf, inf, d.fate);
+            } else {
+                break;
+            }
+        }
+        if (usable && e < n_elements && e == P.first_lens && F.n + 1 <= CMT_MAX_FILTER_PLANES)
+            circle(P.el[e].z0, P.el[e].p[0], P.el[e].fate);      // "Lens entrance"
+        else if (usable && e == n_elements)
+            F.covers_all = 1;
+        if (!usable) { F.n = 0; F.covers_all = 0; }
+    }
+
     bl->tab_bytes = (size_t)tab_total * sizeof(double4);
     if (tab_total > 0) {
         std::vector<double4> h((size_t)tab_total);

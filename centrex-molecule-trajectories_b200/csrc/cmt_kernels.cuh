@@ -108,6 +108,79 @@ __device__ __forceinline__ void retire(bool done, int fate, const Mol &m, int64_
 // ---------------------------------------------------------------------------
 // walk kernel
 // ---------------------------------------------------------------------------
+// The binary64 walk of one molecule per lane (all 32 lanes of the warp must call it; `valid`
+// selects the lanes that carry a molecule): source, every element up to and including the first
+// lens' entrance plane, retirement or hand-over to the lens queue.
+template <bool PHILOX, bool CONTRACT, bool MESH>
+__device__ __forceinline__ void walk_exact(const Params &P, const cmt_source_t &S, uint64_t seed,
+                                           const double *__restrict__ ic, int64_t ic_ld, int64_t first_index,
+                                           const cmt_outputs_t &O, const Queue &Q, BlockAcc &acc, int n_walk,
+                                           int64_t i, bool valid, unsigned &rows_total, unsigned &entries)
+{
+    Mol m;
+    if (valid) {
+        if (PHILOX) {
+            draw(S, seed, (uint64_t)(first_index + i), m);
+        } else {
+            m.x = ic[0 * ic_ld + i]; m.y = ic[1 * ic_ld + i]; m.z = ic[2 * ic_ld + i];
+            m.vx = ic[3 * ic_ld + i]; m.vy = ic[4 * ic_ld + i]; m.vz = ic[5 * ic_ld + i];
+        }
+        // a literal -0.0 becomes +0.0, as the reference's first "+ a*dt" does
+        m.x = add(m.x, 0.0); m.z = add(m.z, 0.0); m.vx = add(m.vx, 0.0); m.vz = add(m.vz, 0.0);
+    } else {
+        m.x = m.y = m.z = m.vx = m.vy = 0.0; m.vz = 1.0;
+    }
+    mol_begin<CONTRACT>(m, P.g);
+
+    CountRowsT<CONTRACT, MESH> rec;
+    int fate = -1;
+    bool to_lens = false;
+    if (valid) {
+        // leading circular planes: tight loop, no element dispatch
+#pragma unroll 1
+        for (int p = 0; p < P.fast.n; ++p) {
+            to_plane(m, P.fast.z[p], P.g, rec);
+            if (outside_radius<CONTRACT>(m, P.fast.T[p])) { fate = P.fast.fate[p]; break; }
+        }
+        if (fate < 0) {
+            if (P.fast.ends_at_lens) {
+                to_lens = true;
+            } else {
+                for (int e = P.fast.next_element; e < n_walk; ++e) {
+                    const DevElement &E = P.el[e];
+                    if (E.type == CMT_LENS) {
+                        to_plane(m, E.z0, P.g, rec);
+                        if (outside_radius<CONTRACT>(m, E.p[0])) fate = E.fate;   // "Lens entrance"
+                        else to_lens = true;
+                        break;
+                    }
+                    fate = do_aperture(E, m, P.g, rec);
+                    if (fate >= 0) break;
+                }
+                if (fate < 0 && !to_lens) fate = P.fate_detected;
+            }
+        }
+    }
+    rows_total += rec.n;
+    entries += to_lens ? 1u : 0u;
+
+    // survivors -> lens queue (compacted)
+    const long long qpos = warp_append(to_lens, Q.count);
+    if (to_lens && qpos < Q.cap) {
+        double *q = Q.q + qpos;
+        q[0 * Q.cap] = m.x;  q[1 * Q.cap] = m.y;  q[2 * Q.cap] = m.z;
+        q[3 * Q.cap] = m.vx; q[4 * Q.cap] = m.vy; q[5 * Q.cap] = m.vz;
+        q[6 * Q.cap] = m.t;
+        q[7 * Q.cap] = __longlong_as_double(i);
+    }
+    retire(valid && !to_lens, fate, m, i, first_index + i, acc, O);
+}
+
+// With the FP32 fate filter (cmt_device.cuh, filter_fate): every molecule is first judged in single
+// precision straight from its initial conditions; the decided ones (99.3 % for the CeNTREX source)
+// retire at once, the others -- survivors bound for the lens and near misses of an edge -- are
+// parked in a per-warp shared-memory ring and walked in binary64 32 at a time, on full warps.
+// The filter needs nothing but fates, so it is skipped when final rows are requested.
 template <bool PHILOX, bool CONTRACT, bool MESH>
 __global__ void __launch_bounds__(WALK_THREADS)
 walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source_t S, uint64_t seed,
@@ -115,75 +188,70 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
             const __grid_constant__ cmt_outputs_t O, Queue Q)
 {
     __shared__ BlockAcc acc;
+    __shared__ int64_t ring[WALK_THREADS / 32][64];
     block_acc_init(acc);
 
     const int n_walk = P.first_lens < P.n_el ? P.first_lens + 1 : P.n_el;
     const int64_t n_tiles = (n + WALK_THREADS - 1) / WALK_THREADS;
-    unsigned rows_total = 0, entries = 0;
+    const bool filt = P.filt.n > 0 && O.final_state == nullptr && !(P.flags & CMT_FLAG_NO_FILTER);
+    unsigned rows_total = 0, entries = 0, filtered = 0;
+    int64_t *my_ring = ring[threadIdx.x >> 5];
+    int pending = 0;                                  // warp-uniform
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t i = tile * WALK_THREADS + threadIdx.x;
-        const bool valid = i < n;
-        Mol m;
-        if (valid) {
-            if (PHILOX) {
-                draw(S, seed, (uint64_t)(first_index + i), m);
-            } else {
-                m.x = ic[0 * ic_ld + i]; m.y = ic[1 * ic_ld + i]; m.z = ic[2 * ic_ld + i];
-                m.vx = ic[3 * ic_ld + i]; m.vy = ic[4 * ic_ld + i]; m.vz = ic[5 * ic_ld + i];
-            }
-            // a literal -0.0 becomes +0.0, as the reference's first "+ a*dt" does
-            m.x = add(m.x, 0.0); m.z = add(m.z, 0.0); m.vx = add(m.vx, 0.0); m.vz = add(m.vz, 0.0);
-        } else {
-            m.x = m.y = m.z = m.vx = m.vy = 0.0; m.vz = 1.0;
-        }
-        mol_begin<CONTRACT>(m, P.g);
-
-        CountRowsT<CONTRACT, MESH> rec;
-        int fate = -1;
-        bool to_lens = false;
-        if (valid) {
-            // leading circular planes: tight loop, no element dispatch
-#pragma unroll 1
-            for (int p = 0; p < P.fast.n; ++p) {
-                to_plane(m, P.fast.z[p], P.g, rec);
-                if (outside_radius<CONTRACT>(m, P.fast.T[p])) { fate = P.fast.fate[p]; break; }
-            }
-            if (fate < 0) {
-                if (P.fast.ends_at_lens) {
-                    to_lens = true;
-                } else {
-                    for (int e = P.fast.next_element; e < n_walk; ++e) {
-                        const DevElement &E = P.el[e];
-                        if (E.type == CMT_LENS) {
-                            to_plane(m, E.z0, P.g, rec);
-                            if (outside_radius<CONTRACT>(m, E.p[0])) fate = E.fate;   // "Lens entrance"
-                            else to_lens = true;
-                            break;
-                        }
-                        fate = do_aperture(E, m, P.g, rec);
-                        if (fate >= 0) break;
-                    }
-                    if (fate < 0 && !to_lens) fate = P.fate_detected;
+    // One turn of the loop either judges a fresh tile in FP32 or walks up to 32 parked molecules in
+    // binary64 (a single call site of walk_exact keeps the kernel small).  Everything that steers
+    // the loop is warp-uniform.
+    int64_t tile = blockIdx.x;
+    for (;;) {
+        int64_t j = 0;
+        bool act = false;
+        if (filt && pending >= 32) {
+            __syncwarp();
+            pending -= 32;
+            j = my_ring[pending + lane_id()];
+            act = true;
+            __syncwarp();
+        } else if (tile < n_tiles) {
+            const int64_t i = tile * WALK_THREADS + threadIdx.x;
+            const bool valid = i < n;
+            tile += gridDim.x;
+            if (filt) {
+                int fate = -1, rows = 0;
+                if (valid) {
+                    FiltIn q;
+                    if (PHILOX) q = draw_f32(S, seed, (uint64_t)(first_index + i));
+                    else q = filter_input(ic[0 * ic_ld + i], ic[1 * ic_ld + i], ic[2 * ic_ld + i],
+                                          ic[3 * ic_ld + i], ic[4 * ic_ld + i], ic[5 * ic_ld + i]);
+                    fate = filter_fate(P.filt, P.fate_detected, q, rows);
                 }
-            }
-        }
-        rows_total += rec.n;
-        entries += to_lens ? 1u : 0u;
+                const bool decided = valid && fate >= 0;
+                if (decided) { rows_total += rows; ++filtered; }
+                Mol none;
+                none.x = none.y = none.z = none.vx = none.vy = none.vz = none.ax = none.ay = none.t = 0.0;
+                retire(decided, fate, none, i, first_index + i, acc, O);
 
-        // survivors -> lens queue (compacted)
-        const long long qpos = warp_append(to_lens, Q.count);
-        if (to_lens && qpos < Q.cap) {
-            double *q = Q.q + qpos;
-            q[0 * Q.cap] = m.x;  q[1 * Q.cap] = m.y;  q[2 * Q.cap] = m.z;
-            q[3 * Q.cap] = m.vx; q[4 * Q.cap] = m.vy; q[5 * Q.cap] = m.vz;
-            q[6 * Q.cap] = m.t;
-            q[7 * Q.cap] = __longlong_as_double(i);
+                const bool need = valid && fate < 0;
+                const unsigned mask = __ballot_sync(0xffffffffu, need);
+                if (need) my_ring[pending + __popc(mask & ((1u << lane_id()) - 1u))] = i;
+                pending += __popc(mask);
+                continue;
+            }
+            j = i;
+            act = valid;
+        } else if (pending > 0) {
+            __syncwarp();
+            act = (int)lane_id() < pending;
+            j = act ? my_ring[lane_id()] : 0;
+            pending = 0;
+        } else {
+            break;
         }
-        retire(valid && !to_lens, fate, m, i, first_index + i, acc, O);
+        walk_exact<PHILOX, CONTRACT, MESH>(P, S, seed, ic, ic_ld, first_index, O, Q, acc, n_walk, j, act,
+                                           rows_total, entries);
     }
     warp_add_work(acc, 0, rows_total);
     warp_add_work(acc, 3, entries);
+    warp_add_work(acc, 5, filtered);
     block_acc_flush(acc, P, O);
 }
 

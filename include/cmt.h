@@ -119,7 +119,8 @@ typedef struct cmt_outputs {
     int64_t final_ld;       /* leading dimension of final_state (>= n) */
     int64_t *counters;      /* [n_fates] per-fate counts, ACCUMULATED (Counter, trajectory_simulator.py:106-124); required */
     int64_t *work;          /* [CMT_WORK_SLOTS] accumulated: ballistic rows, lens RK steps, table out-of-range
-                             * evaluations, lens entries, RK steps that took the plain-intrinsic path, 3 reserved; or NULL */
+                             * evaluations, lens entries, RK steps that took the plain-intrinsic path, molecules whose
+                             * fate the FP32 filter of the walk kernel decided, 2 reserved; or NULL */
     int64_t *saved_index;   /* [saved_capacity] global indices of molecules whose fate is in save_mask (unordered), or NULL */
     int64_t *saved_count;   /* [1] accumulated cursor into saved_index (may exceed capacity: then the list is truncated) */
     int64_t saved_capacity;
@@ -240,7 +241,8 @@ int cmt_fp64_peak(int device, double *dfma_per_s, double *dadd_per_s);
 int cmt_selftest(int device, int64_t n, uint64_t seed, int mode, int64_t out[5]);
 
 /* Debug switch read by cmt_beamline_create: bit 0 forces the plain-intrinsic
- * arithmetic (no shared reciprocals) so both variants can be compared.
+ * arithmetic (no shared reciprocals), bit 1 switches the FP32 fate filter of the walk
+ * kernel off, so each variant can be compared with the plain one.
  * Returns the previous value; a negative argument only queries. */
 int cmt_debug_flags(int flags);
 
