@@ -213,7 +213,7 @@ def run_ours(args):
         return float(t.item())
 
     bl, vdist, xdist = build_workload()
-    prop = eng.Propagator(bl.elements, local)
+    prop = eng.Propagator(bl.elements, local, n_slots=args.slots)
     source = eng.make_source(vdist, xdist)
     n = int(args.molecules)
     seed = 2026
@@ -306,7 +306,7 @@ def run_ours(args):
     # workload, same two passes, reported beside the default; not the headline ----
     contracted = None
     if not args.no_contracted:
-        propc = eng.Propagator(bl.elements, local, math="contracted")
+        propc = eng.Propagator(bl.elements, local, n_slots=args.slots, math="contracted")
         for _ in range(warm):
             propc.reset()
             resc = propc.propagate_ic(ic, first_index=first, want_fate=True)
@@ -500,6 +500,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap", action="store_true", help="issue every step on one stream")
     ap.add_argument("--no-contracted", action="store_true", help="skip the contracted-arithmetic pass")
+    ap.add_argument("--slots", type=int, default=3, help="streams the overlapped steps alternate over")
     ap.add_argument("--no-graphs", action="store_true", help="launch the overlapped steps individually instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":

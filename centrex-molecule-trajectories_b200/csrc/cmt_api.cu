@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -740,7 +741,11 @@ extern "C" int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t 
     // one launch pair per 2^26 molecules (4.3 GB of queue workspace per stream): splitting a run
     // further was measured slower (the lens integrator of a small chunk cannot keep its lanes
     // refilled); consecutive chunks alternate streams
-    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 26);
+    int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 26);
+    if (const char *env = getenv("CMT_PHILOX_CHUNK")) {          // experiments only
+        const long long v = atoll(env);
+        if (v > 0) chunk = std::min<int64_t>(n, (int64_t)v);
+    }
     int rc = pipe_prepare(p, bl, chunk, false, false, false);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(p.d_cnt, 0, (CMT_MAX_FATES + CMT_WORK_SLOTS) * sizeof(int64_t), p.st[0]));
@@ -764,7 +769,7 @@ extern "C" int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t 
 // ---------------------------------------------------------------------------
 extern "C" int cmt_selftest(int device, int64_t n, uint64_t seed, int mode, int64_t out[5])
 {
-    if (!out || n < 0 || mode < 0 || mode > 2) return fail(CMT_EINVAL, "bad selftest arguments");
+    if (!out || n < 0 || mode < 0 || mode > 3) return fail(CMT_EINVAL, "bad selftest arguments");
     DeviceGuard guard(device);
     CUDA_TRY(guard.status);
     unsigned long long *d = nullptr;

@@ -518,6 +518,20 @@ __global__ void __launch_bounds__(256) selftest_kernel(int64_t n, uint64_t seed,
             a = random_double(s, -60, 20, true);
             b = 6.0;
             sq = random_double(s, -200, 200, false);
+        } else if (mode == 3) {     // a / sqrt(sq) through the square root's own reciprocal estimate
+            a = random_double(s, -60, 20, true);
+            sq = random_double(s, -60, 20, false);
+            bool ok3 = true;
+            double yr, early;
+            const double r = sqrt_rcp_fast(sq, ok3, yr, early);
+            const double q = div_rcp_mid(a, r, yr, ok3);
+            if (ok3) {
+                ++c[0];
+                if (__double_as_longlong(q) != __double_as_longlong(__ddiv_rn(a, __dsqrt_rn(sq)))) ++c[1];
+                ++c[2];
+                if (__double_as_longlong(r) != __double_as_longlong(__dsqrt_rn(sq))) ++c[3];
+            }
+            continue;
         } else {                    // everything, including the fallback ranges
             a = random_double(s, -1022, 1023, true);
             b = random_double(s, -1022, 1023, true);

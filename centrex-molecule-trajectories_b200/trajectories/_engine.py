@@ -20,6 +20,7 @@ DEFAULT_CHUNK = 1 << 26          # molecules per launch: 4.3 GB of lens-queue wo
                                  # launches keep the lens integrator's lanes refilled (1e10 molecules: 0.81 s at
                                  # 2^24, 0.73 s at 2^26)
 ROW_BUDGET_BYTES = 1 << 30       # device bytes per saved-trajectory batch
+PINNED_RESULT_BYTES = 2 << 30    # saved-trajectory blocks up to this size are returned in page-locked memory
 
 
 def _torch():
@@ -473,13 +474,23 @@ class Propagator:
         torch.cumsum(n_rows, 0, out=offsets[1:])
         off_np = offsets.cpu().numpy()
         total_rows = int(off_np[-1])
-        rows_out = np.empty((total_rows, nat.CMT_ROW_DOUBLES), dtype=np.float64)
+        # Result block.  Up to PINNED_RESULT_BYTES it is page-locked memory from torch's caching host
+        # allocator: the device copies straight into the array the caller receives (no staging, no
+        # host-side copy, no first-touch page faults), and the block returns to the allocator's pool
+        # when the last Molecule viewing it is dropped, so a loop of runs re-uses the same pages.
+        # Larger results (or a failed page-lock) go through two reusable pinned staging buffers into
+        # ordinary memory.
+        host = None
+        if 0 < total_rows * nat.CMT_ROW_DOUBLES * 8 <= PINNED_RESULT_BYTES:
+            try:
+                host = torch.empty((total_rows, nat.CMT_ROW_DOUBLES), dtype=torch.float64, pin_memory=True)
+            except RuntimeError:
+                host = None
+        rows_out = host.numpy() if host is not None else np.empty((total_rows, nat.CMT_ROW_DOUBLES), dtype=np.float64)
 
-        # pass 2: rows, in batches bounded by the device row budget; each batch comes back through two
-        # reusable pinned staging buffers (page-locking a fresh result block per run costs far more than
-        # the copy: ~0.4 ms per MB), the D2H of one piece overlapping the host copy-out of the previous one
-        stage = _staging(self.device)
-        stage_rows = stage[0].shape[0]
+        # pass 2: rows, in batches bounded by the device row budget
+        stage = _staging(self.device) if host is None else None
+        stage_rows = stage[0].shape[0] if stage is not None else 0
         pending = None                     # (event, staging index, destination slice)
 
         def drain():
@@ -503,6 +514,13 @@ class Propagator:
                 sel_ptr, st = None, state[:, lo:hi]
             self._traj_call(hi - lo, st, n_comp, sel_ptr, select_base, rows.data_ptr(), rel.data_ptr(),
                             n_rows[lo:hi], fate[lo:hi])
+            if host is not None:
+                if n_batch_rows:
+                    host[base:base + n_batch_rows].copy_(rows[:n_batch_rows], non_blocking=True)
+                lo = hi
+                continue
+            # each piece comes back through a pinned staging buffer, the D2H of one piece overlapping
+            # the host copy-out of the previous one
             for r0 in range(0, n_batch_rows, stage_rows):
                 r1 = min(n_batch_rows, r0 + stage_rows)
                 b = piece & 1
@@ -519,6 +537,8 @@ class Propagator:
                 piece += 1
             drain()                            # the device buffer is released before the next batch
             lo = hi
+        if host is not None:
+            torch.cuda.current_stream(self.device).synchronize()
         return rows_out, off_np, fate.cpu().numpy()
 
 

@@ -106,6 +106,21 @@ def test_golden_trajectory_rows(torch_cuda, golden_dir):
         engmod.ROW_BUDGET_BYTES = old_budget
     np.testing.assert_array_equal(offs3, offs)
     np.testing.assert_array_equal(rows3, rows)
+    # results too large to page-lock come back through the staging buffers into ordinary memory
+    old_pinned, old_budget = engmod.PINNED_RESULT_BYTES, engmod.ROW_BUDGET_BYTES
+    engmod.PINNED_RESULT_BYTES, engmod.ROW_BUDGET_BYTES = 0, 2000 * 80
+    try:
+        rows4, offs4, fate4 = prop.trajectories(full, select=sel, select_base=1000)
+    finally:
+        engmod.PINNED_RESULT_BYTES, engmod.ROW_BUDGET_BYTES = old_pinned, old_budget
+    np.testing.assert_array_equal(offs4, offs)
+    np.testing.assert_array_equal(rows4, rows)
+    # the page-locked block lives as long as any view of it and is recycled afterwards
+    view = rows[offs[1]:offs[2]].copy(), rows[offs[1]:offs[2]]
+    del rows, rows2, rows3
+    for _ in range(3):
+        prop.trajectories(full, select=sel, select_base=1000)
+    np.testing.assert_array_equal(view[1], view[0])
 
 
 @pytest.mark.parametrize("n,seed,sigma", [(200000, 11, 39.5), (60000, 12, 4.0), (257, 13, 4.0), (1, 14, 4.0), (33, 15, 1.0)])
