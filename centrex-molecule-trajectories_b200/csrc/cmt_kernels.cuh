@@ -289,10 +289,11 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
     int n_steps = 0;        // of lens e
     double bore_T = 0.0;    // of lens e
     double r_last = 0.0;    // last abscissa of its table (contracted mode)
+    double s_xy = 0.0;      // x*x + y*y of the current position while inside a lens (exact mode)
     bool have = false;
     bool drained = false;   // warp-uniform: the queue has nothing left
     Table tb;
-    tb.t = smem_tab; tb.n = 2; tb.inv_h = 0.0;
+    tb.t = smem_tab; tb.n = 2; tb.inv_h = 0.0; tb.inv_h_f = 0.f;
     LensConsts lc;
     lc.dt = 0.0; lc.zinc = 0.0;
 
@@ -321,6 +322,7 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
                         tb = table_of(E, smem_tab);
                         r_last = tb.t[tb.n - 1].x;
                         lc = lens_consts<CONTRACT>(E, m);
+                        s_xy = radius_sq(m.x, m.y);
                         have = true;
                     }
                 }
@@ -338,12 +340,12 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
                 for (int b = 0; b < LENS_BURST; ++b) {
                     int oob = 0;
                     if (CONTRACT) lens_step_contracted(tb, r_last, lc, m, P.g, oob);
-                    else lens_step(tb, lc, r6, m, P.g, oob, reference_math);
+                    else lens_step(tb, lc, r6, m, s_xy, P.g, oob, reference_math);
                     oob_total += oob & 0xffff;
                     ref_total += oob >> 16;
                     ++steps_total;
                     ++step;
-                    if (outside_radius<CONTRACT>(m, bore_T)) { fate = P.el[e].fate2; break; }   // "Inside lens"
+                    if (CONTRACT ? outside_radius<CONTRACT>(m, bore_T) : (s_xy > bore_T)) { fate = P.el[e].fate2; break; }   // "Inside lens"
                     if (step >= n_steps) {
                         lens_exit(P.el[e], m, P.g, rec);
                         step = -1;
@@ -363,6 +365,7 @@ lens_kernel(const __grid_constant__ Params P, int64_t first_index,
                         tb = table_of(E, smem_tab);
                         r_last = tb.t[tb.n - 1].x;
                         lc = lens_consts<CONTRACT>(E, m);
+                        s_xy = radius_sq(m.x, m.y);
                         if (E.n_steps <= 0) { lens_exit(E, m, P.g, rec); step = -1; ++e; }
                     }
                 } else {

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Parity of the CUDA path with the CPU oracle at sizes beyond the test suite (one-off, round 1).
+"""Parity of the CUDA path with the CPU oracle at sizes beyond the test suite (round 1).
 
     python profiles/parity_at_scale.py > profiles/r01_parity_at_scale.json
 """
@@ -39,7 +39,16 @@ def compare(label, bl, vdist, xdist, n, seed, math="exact"):
     same = fate == want["fate"]
     rel = np.abs(fin[:, same] - want["fin"][:, same]) / np.maximum(np.abs(want["fin"][:, same]), 1e-9)
     bit = (fin[:, same].view(np.int64) == want["fin"][:, same].view(np.int64)).mean()
-    out = dict(case=label, math=math, molecules=n, lens_entries=int(want["work"][1] > 0) and int(res.work[3]),
+    # the same molecules again asking for fates only: that launch runs the walk kernel's FP32 fate filter
+    prop.reset()
+    res2 = prop.propagate_ic(torch.from_numpy(ic).cuda(), want_fate=True, want_final=False)
+    torch.cuda.synchronize()
+    fate2 = res2.fate.cpu().numpy()
+    filt = dict(filter_decided=int(res2.work[5]), filter_fate_mismatches_vs_oracle=int((fate2 != want["fate"]).sum()),
+                filter_fates_equal_unfiltered=bool((fate2 == fate).all()),
+                filter_counters_equal=bool((res2.counters.cpu().numpy() == want["counters"]).all()),
+                filter_rows_steps_equal=bool((res2.work[:2].cpu().numpy() == want["work"][:2]).all()))
+    out = dict(case=label, math=math, molecules=n, **filt, lens_entries=int(want["work"][1] > 0) and int(res.work[3]),
                rk_steps=int(want["work"][1]), fate_mismatches=int((~same).sum()), max_rel_err=float(rel.max()),
                bit_identical_fraction=float(bit), counters_equal=bool((res.counters.cpu().numpy() == want["counters"]).all()),
                oracle_seconds=round(t_cpu, 2), oracle_threads=threads)
