@@ -77,6 +77,13 @@ static LensFn lens_variant(bool contract, bool mesh)
 // ---------------------------------------------------------------------------
 // beamline handle
 // ---------------------------------------------------------------------------
+struct PlaneD {
+    double z;
+    int kind, fate;
+    double T;        // circle: squared-radius threshold
+    double e[4];     // box: x1, x2, y1, y2
+};
+
 struct cmt_beamline {
     Params P;
     int device;
@@ -86,6 +93,7 @@ struct cmt_beamline {
     double4 *d_tab;     // [tab_total]: (r_j, r_{j+1}, a_j, slope_j)
     size_t tab_bytes;   // dynamic shared memory the lens/trajectory kernels need
     bool has_mesh;      // a Honeycomb is present: launch the kernel variants that carry its hit test
+    std::vector<struct PlaneD> planes;   // the filter planes in binary64 (thresholds of the quick filter derive from them)
 };
 
 // Largest double s with sqrt(s) <= R under round-to-nearest, so that the
@@ -104,6 +112,108 @@ static double radius_threshold(double R)
         if (su <= R) c = up; else break;
     }
     return c;
+}
+
+// ---------------------------------------------------------------------------
+// Thresholds of the quick filter (cmt_device.cuh: quick_fate), in binary64, rounded outwards.
+//
+// Error model as in filter_fate, u = 2^-24: for a molecule with input errors e_* and 1/vz known to
+// relv = e_vz/|vz| + 4u, the single-precision position at plane p is off by at most E/2 per coordinate,
+//   E = c0 + c1 dtE + c2 dtE^2,  dtE = (|z_p| + |z_0|)/|vz|,
+//   c0 = 2 (e_x0 + e_y0 + 2u (|x0| + |y0|)),  c1 = 2 ((|vx| + |vy|)(relv + 6u) + e_vx + e_vy),  c2 = 4 g (relv + 3u).
+// quick_fate evaluates x = bx + sx z, y = A + B z + C z^2 with sx = vx/vz etc.; term by term its
+// roundings are bounded by the same expression with 8u and 4u in place of 6u and 3u (slope: relv + u,
+// intercept: one more rounding of |x0| + |sx z0|, plane position: u |z_p|; gravity: 2 relv + 8u on
+// g (|z_p| + |z_0|)^2 / (2 vz^2)).  The guards pos_g .. ex_g bound every molecule-dependent factor:
+//   c0 <= k0 = 2 (ex_g + 2u pos_g),  c1/|vz| <= k1 = 2 (ang_g (relv + 8u) + eva_g),  c2/vz^2 <= k2 = 4 g (relv + 4u) ainv_g^2,
+// hence E <= eps_p = k0 + k1 Z_p + k2 Z_p^2 with Z_p = |z_p| + z0_g.
+// Circle: |s32 - s| <= B(s32) = 2 (sqrt(2 s32 (1 + 4u)) + eps) eps + 8u s32 (twice the first-order bound, as in
+// filter_fate, with |x| + |y| <= sqrt(2 (x^2 + y^2))).  B is increasing, so  s32 < T_lo := T - B(T)  implies s < T, and
+// s32 > T_hi with T_hi - B(T_hi) >= T implies s > T (s - B(s) is increasing beyond 2 eps^2; T_hi >= 16 eps^2 is required).
+// Box: the edges move by eps + 2^-21 max|edge| inwards (surely inside) and outwards (surely outside).
+// Guard values: replayed inputs carry e_q = u |q|, so only pos_g, z0_g, ang_g, ainv_g actually select;
+// for the Philox source the e_* guards are four times the typical error of draw_f32 (a molecule with a
+// larger one is undecided, like one with (|vx| + |vy|) > 2 |vz| or slower than 8 sqrt(2 g Z)).
+// ---------------------------------------------------------------------------
+static float float_down(double x)
+{
+    float f = (float)x;
+    if ((double)f > x) f = std::nextafterf(f, -std::numeric_limits<float>::infinity());
+    return f;
+}
+static float float_up(double x)
+{
+    float f = (float)x;
+    if ((double)f < x) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+    return f;
+}
+
+static void build_quick(const std::vector<PlaneD> &planes, double g, const cmt_source_t *S, QuickFilter &Q)
+{
+    memset(&Q, 0, sizeof(Q));
+    if (planes.empty()) return;
+    const double u = std::ldexp(1.0, -24);
+    const double inf = std::numeric_limits<double>::infinity();
+    double lxy = 0, zmin = inf, zmax = 0;
+    for (const PlaneD &p : planes) {
+        zmax = std::max(zmax, std::fabs(p.z));
+        zmin = std::min(zmin, std::fabs(p.z));
+        if (p.kind == CMT_FILTER_CIRCLE) lxy = std::max(lxy, std::sqrt(p.T));
+        else for (double v : p.e) if (std::isfinite(v)) lxy = std::max(lxy, std::fabs(v));
+    }
+    const double pos_g = 4 * lxy, ang_g = 2.0;
+    double z0_g, ex_g, eva_g, relvz_g;
+    if (!S) {
+        z0_g = 2 * zmin;
+        ex_g = 1.01 * u * pos_g; eva_g = 1.01 * u * ang_g; relvz_g = 1.01 * u;
+    } else {
+        const double en = std::ldexp(1.0, -18) * (2 * 1.25 + 0.8), k = 4.0, r22 = std::ldexp(1.0, -22);
+        const double sxy = std::fabs(S->vsigma[0]) + std::fabs(S->vsigma[1]), sz = std::fabs(S->vsigma[2]);
+        const double mz = std::fabs(S->vmean[2]);
+        const double vref = std::max(mz - 2 * sz, 0.5 * mz);
+        if (!(vref > 0) || !std::isfinite(vref) || !std::isfinite(sxy) || !std::isfinite(S->z)) return;
+        z0_g = std::fabs(S->z) * (1 + 4 * u) + 1e-30;
+        eva_g = k * (sxy * en + r22 * (std::fabs(S->vmean[0]) + std::fabs(S->vmean[1]) + 1.25 * sxy)) / vref;
+        relvz_g = k * (sz * en + r22 * (mz + 1.25 * sz)) / vref;
+        ex_g = S->pos_kind == CMT_POS_DISC ? k * 2 * std::ldexp(1.0, -18) * std::fabs(S->p0)
+                                           : k * (std::fabs(S->p0) + std::fabs(S->p1)) * (en + 1.25 * r22);
+    }
+    const double zsum = zmax + z0_g;
+    const double vmin = 8 * std::sqrt(2 * std::fabs(g) * zsum);
+    const double ainv_g = vmin > 1e-12 ? 1 / vmin : 1e12;
+    const double relv = relvz_g * 1.001 + 4 * u;
+    const double k0 = 2 * (ex_g + 2 * u * pos_g), k1 = 2 * (ang_g * (relv + 8 * u) + eva_g);
+    const double k2 = 4 * std::fabs(g) * (relv + 4 * u) * ainv_g * ainv_g;
+    if (!(std::isfinite(k0) && std::isfinite(k1) && std::isfinite(k2))) return;
+    for (size_t i = 0; i < planes.size(); ++i) {
+        const PlaneD &p = planes[i];
+        QuickPlane &q = Q.pl[i];
+        const double Z = std::fabs(p.z) + z0_g;
+        const double eps = (k0 + k1 * Z + k2 * Z * Z) * (1 + std::ldexp(1.0, -10));
+        q.z = (float)p.z; q.kind = p.kind; q.fate = p.fate;
+        if (p.kind == CMT_FILTER_CIRCLE) {
+            auto B = [&](double s) { return 2 * (std::sqrt(2 * s * (1 + 4 * u)) + eps) * eps + 8 * u * s + 1e-37; };
+            const double T_lo = p.T - B(p.T);
+            double T_hi = p.T + B(p.T);
+            for (int it = 0; it < 6; ++it) T_hi = p.T + B(T_hi);
+            T_hi *= 1 + std::ldexp(1.0, -20);
+            if (!(T_lo >= 0.5 * p.T) || !(T_hi >= 16 * eps * eps) || !(T_hi <= 2 * p.T)) return;
+            q.v[0] = float_down(T_lo);
+            q.v[1] = float_up(T_hi);
+        } else {
+            double m = 0;
+            for (double v : p.e) if (std::isfinite(v)) m = std::max(m, std::fabs(v));
+            const double eb = eps + std::ldexp(m, -21) + 1e-37;
+            q.v[0] = float_up(p.e[0] + eb);   q.v[1] = float_down(p.e[1] - eb);
+            q.v[2] = float_up(p.e[2] + eb);   q.v[3] = float_down(p.e[3] - eb);
+            q.v[4] = float_down(p.e[0] - eb); q.v[5] = float_up(p.e[1] + eb);
+            q.v[6] = float_down(p.e[2] - eb); q.v[7] = float_up(p.e[3] + eb);
+            if (!(q.v[0] < q.v[1]) || !(q.v[2] < q.v[3])) return;
+        }
+    }
+    Q.pos_g = float_down(pos_g); Q.z0_g = float_down(z0_g); Q.ainv_g = float_down(ainv_g); Q.ang_g = float_down(ang_g);
+    Q.eva_g = float_down(eva_g); Q.relvz_g = float_down(relvz_g); Q.ex_g = float_down(ex_g);
+    Q.usable = 1;
 }
 
 extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements, const cmt_table_t *tables,
@@ -260,6 +370,7 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
             pl.z = (float)z; pl.kind = CMT_FILTER_CIRCLE; pl.fate = fate;
             pl.a = (float)T; pl.b = pl.c = pl.d = 0.f;
             pl.tol = std::ldexp(std::fabs(pl.a), -21) + 1e-37f;
+            bl->planes.push_back(PlaneD{z, CMT_FILTER_CIRCLE, fate, T, {0, 0, 0, 0}});
         };
         auto box = [&](double z, double x1, double x2, double y1, double y2, int fate) {
             if (!(ordinary(z) && edge_ok(x1) && edge_ok(x2) && edge_ok(y1) && edge_ok(y2))) { usable = false; return; }
@@ -269,6 +380,7 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
             float m = 0.f;
             for (float v : {pl.a, pl.b, pl.c, pl.d}) if (std::isfinite(v)) m = std::max(m, std::fabs(v));
             pl.tol = std::ldexp(m, -21) + 1e-37f;
+            bl->planes.push_back(PlaneD{z, CMT_FILTER_BOX, fate, 0.0, {x1, x2, y1, y2}});
         };
         int e = 0;
         for (; usable && e < n_elements && F.n + 2 <= CMT_MAX_FILTER_PLANES; ++e) {
@@ -291,7 +403,8 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
             circle(P.el[e].z0, P.el[e].p[0], P.el[e].fate);      // "Lens entrance"
         else if (usable && e == n_elements)
             F.covers_all = 1;
-        if (!usable) { F.n = 0; F.covers_all = 0; }
+        if (!usable) { F.n = 0; F.covers_all = 0; bl->planes.clear(); }
+        build_quick(bl->planes, g, nullptr, P.quick);          // replayed initial conditions; Philox launches rebuild it
     }
 
     bl->tab_bytes = (size_t)tab_total * sizeof(double4);
@@ -491,8 +604,15 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
             {{walk_kernel<true, false, false>, walk_kernel<true, false, true>},
              {walk_kernel<true, true, false>, walk_kernel<true, true, true>}}};
         const bool contract = bl->math == CMT_MATH_CONTRACTED;
-        walk[philox][contract][bl->has_mesh]<<<grid_walk, WALK_THREADS, 0, st>>>(
-            bl->P, S, seed, philox ? nullptr : ic, philox ? 0 : ic_ld, n, first_index, *out, Q);
+        if (philox && bl->P.filt.n > 0) {
+            // the quick filter's thresholds depend on the source's error bounds: per launch, by value
+            Params P = bl->P;
+            build_quick(bl->planes, bl->P.g, &S, P.quick);
+            walk[1][contract][bl->has_mesh]<<<grid_walk, WALK_THREADS, 0, st>>>(P, S, seed, nullptr, 0, n, first_index, *out, Q);
+        } else {
+            walk[philox][contract][bl->has_mesh]<<<grid_walk, WALK_THREADS, 0, st>>>(
+                bl->P, S, seed, philox ? nullptr : ic, philox ? 0 : ic_ld, n, first_index, *out, Q);
+        }
     }
     CUDA_TRY(cudaGetLastError());
     if (has_lens) {

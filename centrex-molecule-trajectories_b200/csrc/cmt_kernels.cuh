@@ -194,6 +194,7 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
     const int n_walk = P.first_lens < P.n_el ? P.first_lens + 1 : P.n_el;
     const int64_t n_tiles = (n + WALK_THREADS - 1) / WALK_THREADS;
     const bool filt = P.filt.n > 0 && O.final_state == nullptr && !(P.flags & CMT_FLAG_NO_FILTER);
+    const bool quick = P.quick.usable && !(P.flags & CMT_FLAG_NO_QUICK);
     unsigned rows_total = 0, entries = 0, filtered = 0;
     int64_t *my_ring = ring[threadIdx.x >> 5];
     int pending = 0;                                  // warp-uniform
@@ -222,7 +223,8 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
                     if (PHILOX) q = draw_f32(S, seed, (uint64_t)(first_index + i));
                     else q = filter_input(ic[0 * ic_ld + i], ic[1 * ic_ld + i], ic[2 * ic_ld + i],
                                           ic[3 * ic_ld + i], ic[4 * ic_ld + i], ic[5 * ic_ld + i]);
-                    fate = filter_fate(P.filt, P.fate_detected, q, rows);
+                    fate = quick ? quick_fate(P.filt, P.quick, P.fate_detected, q, rows)
+                                 : filter_fate(P.filt, P.fate_detected, q, rows);
                 }
                 const bool decided = valid && fate >= 0;
                 if (decided) { rows_total += rows; ++filtered; }

@@ -243,7 +243,8 @@ int cmt_selftest(int device, int64_t n, uint64_t seed, int mode, int64_t out[5])
 
 /* Debug switch read by cmt_beamline_create: bit 0 forces the plain-intrinsic
  * arithmetic (no shared reciprocals), bit 1 switches the FP32 fate filter of the walk
- * kernel off, so each variant can be compared with the plain one.
+ * kernel off, bit 2 keeps the filter but without its constant-threshold fast form, so
+ * each variant can be compared with the plain one.
  * Returns the previous value; a negative argument only queries. */
 int cmt_debug_flags(int flags);
 

@@ -243,3 +243,119 @@ def aimed_ics(flat, n, rng, scale, base):
     ic[3] = (xt - ic[0]) / dt
     ic[4] = (yt - ic[1] + 0.5 * oracle.G * dt * dt) / dt
     return ic
+
+
+# ---- the filter with constant thresholds (quick_fate / build_quick) ----
+def _down(x):
+    f = F(x)
+    return np.nextafter(f, F(-np.inf)) if float(f) > x else f
+
+
+def _up(x):
+    f = F(x)
+    return np.nextafter(f, F(np.inf)) if float(f) < x else f
+
+
+def quick_table(flat, source=None, g=oracle.G):
+    """-> dict(guards..., planes=[...]) or None when the thresholds cannot be used (cmt_api.cu: build_quick)."""
+    planes, _ = filter_planes(flat, g)
+    if not planes:
+        return None
+    # binary64 plane data, in the order filter_planes lists them
+    pd = []
+    for t in flat.elements:
+        if t["type"] == oracle.CIRCULAR:
+            pd += [(t["z0"], CIRCLE, t["R"] ** 2, None), (t["z1"], CIRCLE, t["R"] ** 2, None)]
+        elif t["type"] == oracle.RECTANGULAR:
+            pd += [(z, BOX, 0.0, (t["x1"], t["x2"], t["y1"], t["y2"])) for z in (t["z0"], t["z1"])]
+        elif t["type"] == oracle.FIELDPLATES:
+            pd += [(z, BOX, 0.0, (t["x1"], t["x2"], -np.inf, np.inf)) for z in (t["z0"], t["z1"])]
+        else:
+            if t["type"] == oracle.LENS:
+                pd.append((t["z0"], CIRCLE, t["R"] ** 2, None))
+            break
+    pd = pd[:len(planes)]
+    u = 2.0 ** -24
+    lxy = max([np.sqrt(T) if k == CIRCLE else max(abs(v) for v in e if np.isfinite(v)) for _, k, T, e in pd])
+    zmin, zmax = min(abs(z) for z, *_ in pd), max(abs(z) for z, *_ in pd)
+    pos_g, ang_g = 4 * lxy, 2.0
+    if source is None:
+        z0_g, ex_g, eva_g, relvz_g = 2 * zmin, 1.01 * u * pos_g, 1.01 * u * ang_g, 1.01 * u
+    else:
+        s = source[0]
+        en, k, r22 = 2.0 ** -18 * (2 * 1.25 + 0.8), 4.0, 2.0 ** -22
+        sxy, sz, mz = abs(s["vsigma"][0]) + abs(s["vsigma"][1]), abs(s["vsigma"][2]), abs(s["vmean"][2])
+        vref = max(mz - 2 * sz, 0.5 * mz)
+        if not vref > 0:
+            return None
+        z0_g = abs(s["z"]) * (1 + 4 * u) + 1e-30
+        eva_g = k * (sxy * en + r22 * (abs(s["vmean"][0]) + abs(s["vmean"][1]) + 1.25 * sxy)) / vref
+        relvz_g = k * (sz * en + r22 * (mz + 1.25 * sz)) / vref
+        ex_g = k * 2 * 2.0 ** -18 * abs(s["p0"]) if int(s["pos_kind"]) == 0 else k * (abs(s["p0"]) + abs(s["p1"])) * (en + 1.25 * r22)
+    zsum = zmax + z0_g
+    vmin = 8 * np.sqrt(2 * abs(g) * zsum)
+    ainv_g = 1 / vmin if vmin > 1e-12 else 1e12
+    relv = relvz_g * 1.001 + 4 * u
+    k0, k1 = 2 * (ex_g + 2 * u * pos_g), 2 * (ang_g * (relv + 8 * u) + eva_g)
+    k2 = 4 * abs(g) * (relv + 4 * u) * ainv_g ** 2
+    out = []
+    for (z, kind, T, e), pl in zip(pd, planes):
+        Z = abs(z) + z0_g
+        eps = (k0 + k1 * Z + k2 * Z * Z) * (1 + 2.0 ** -10)
+        if kind == CIRCLE:
+            def B(s_):
+                return 2 * (np.sqrt(2 * s_ * (1 + 4 * u)) + eps) * eps + 8 * u * s_ + 1e-37
+            T_lo, T_hi = T - B(T), T + B(T)
+            for _ in range(6):
+                T_hi = T + B(T_hi)
+            T_hi *= 1 + 2.0 ** -20
+            if not (T_lo >= 0.5 * T and T_hi >= 16 * eps * eps and T_hi <= 2 * T):
+                return None
+            v = [_down(T_lo), _up(T_hi)] + [F(0)] * 6
+        else:
+            m = max(abs(x) for x in e if np.isfinite(x))
+            eb = eps + np.ldexp(m, -21) + 1e-37
+            v = [_up(e[0] + eb), _down(e[1] - eb), _up(e[2] + eb), _down(e[3] - eb),
+                 _down(e[0] - eb), _up(e[1] + eb), _down(e[2] - eb), _up(e[3] + eb)]
+            if not (v[0] < v[1] and v[2] < v[3]):
+                return None
+        out.append(dict(z=F(z), kind=kind, fate=pl["fate"], v=v))
+    return dict(pos_g=_down(pos_g), z0_g=_down(z0_g), ainv_g=_down(ainv_g), ang_g=_down(ang_g), eva_g=_down(eva_g),
+                relvz_g=_down(relvz_g), ex_g=_down(ex_g), planes=out)
+
+
+def quick_fate(table, covers_all, fate_detected, q, g=oracle.G):
+    n = q["x0"].shape[0]
+    fate = np.full(n, -1, dtype=np.int32)
+    rows = np.zeros(n, dtype=np.int32)
+    hg = F(0.5 * g)
+    with np.errstate(all="ignore"):
+        inv = F(1) / q["vz"]
+        ainv = np.abs(inv)
+        live = ((np.abs(q["x0"]) + np.abs(q["y0"]) <= table["pos_g"]) & (np.abs(q["z0"]) <= table["z0_g"])
+                & (ainv <= table["ainv_g"]) & ((np.abs(q["vx"]) + np.abs(q["vy"])) * ainv <= table["ang_g"])
+                & ((q["evx"] + q["evy"]) * ainv <= table["eva_g"]) & (q["evz"] * ainv <= table["relvz_g"])
+                & (q["ex0"] + q["ey0"] <= table["ex_g"]))
+        guarded = live.copy()
+        sx, sy, qg = q["vx"] * inv, q["vy"] * inv, hg * inv * inv
+        bx = -sx * q["z0"] + q["x0"]
+        B = F(2) * qg * q["z0"] + sy
+        A = -q["z0"] * (qg * q["z0"] + sy) + q["y0"]
+        for p, pl in enumerate(table["planes"]):
+            x = sx * pl["z"] + bx
+            y = (-qg * pl["z"] + B) * pl["z"] + A
+            v = pl["v"]
+            if pl["kind"] == CIRCLE:
+                s = x * x + y * y
+                dead, ok = s > v[1], s < v[0]
+            else:
+                ok = (x > v[0]) & (x < v[1]) & (y > v[2]) & (y < v[3])
+                dead = (x < v[4]) | (x > v[5]) | (y < v[6]) | (y > v[7])
+            hit = live & dead
+            fate[hit] = pl["fate"]
+            rows[hit] = p + 1
+            live = live & ok & ~dead
+        if covers_all:
+            fate[live] = fate_detected
+            rows[live] = len(table["planes"])
+    return fate, rows, guarded

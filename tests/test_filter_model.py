@@ -94,3 +94,68 @@ def test_single_precision_source_stays_within_its_bounds(pos):
         flat = oracle.flatten(bl.elements)
         frac, _ = judge(flat, ic, fm.draw_f32(src, seed, first, n, rng))
         assert frac > 0.99
+
+
+# ---- the filter with constant thresholds (quick_fate) ----
+def judge_quick(flat, ic, source=None, q=None):
+    want = oracle.propagate(flat, ic)
+    _, covers_all = fm.filter_planes(flat)
+    table = fm.quick_table(flat, source)
+    assert table is not None
+    fate, rows, guarded = fm.quick_fate(table, covers_all, flat.fate_detected, fm.filter_input(ic) if q is None else q)
+    decided = fate >= 0
+    assert not (decided & (fate != want["fate"])).any()
+    assert not (decided & (rows != want["n_rows"] - 1)).any()
+    return decided.mean(), guarded.mean()
+
+
+@pytest.mark.parametrize("name", ["lens", "apertures", "spa"])
+def test_quick_standard_inputs(name):
+    flat = oracle.flatten(beamlines()[name].elements)
+    frac, guarded = judge_quick(flat, standard_ics(400000, 3))
+    assert guarded > 0.999 and frac > (0.993 if name == "lens" else 0.999)
+
+
+@pytest.mark.parametrize("name", ["lens", "apertures", "spa"])
+@pytest.mark.parametrize("scale", [1e-4, 1e-6, 1e-8])
+def test_quick_molecules_aimed_at_the_edges(name, scale):
+    flat = oracle.flatten(beamlines()[name].elements)
+    rng = np.random.default_rng(10 + int(-np.log10(scale)))
+    judge_quick(flat, fm.aimed_ics(flat, 150000, rng, scale, standard_ics(150000, 18)))
+
+
+def test_quick_hostile_and_offset_inputs(golden_dir):
+    flat = oracle.flatten(beamlines()["lens"].elements)
+    ic = np.repeat(standard_ics(64, 9, 3.0), 10, axis=1)
+    k = np.arange(ic.shape[1]) % 10
+    ic[5, k == 1] = 0.0
+    ic[5, k == 2] *= -1
+    ic[0, k == 3] = np.nan
+    ic[4, k == 4] = np.inf
+    ic[5, k == 5] = 1e-300
+    ic[5, k == 6] = 1e300
+    ic[0, k == 7] = 1e200
+    ic[2, k == 8] = -3.0          # far upstream: outside the z0 guard
+    ic[5, k == 9] = 20.0          # slow: gravity matters, outside the velocity guard
+    judge_quick(flat, ic)
+    g = np.load(golden_dir / "edges.npz")
+    for bl in (lens_beamline((g["table_r"], g["table_a"])), apertures_beamline()):
+        judge_quick(oracle.flatten(bl.elements), g["ic"])
+
+
+@pytest.mark.parametrize("pos", ["disc", "gauss"])
+def test_quick_with_the_single_precision_source(pos):
+    from trajectories.distributions import (CeNTREXPositionDistribution, CeNTREXVelocityDistribution,
+                                            GaussianPositionDistribution)
+
+    xdist = CeNTREXPositionDistribution() if pos == "disc" else GaussianPositionDistribution()
+    src = oracle.make_source(CeNTREXVelocityDistribution(), xdist)
+    rng = np.random.default_rng(2)
+    n, seed, first = 400000, 99, 1 << 35
+    ic = oracle.draw(src, seed, first, n)
+    for name, bl in beamlines().items():
+        if (name == "spa") != (pos == "gauss"):
+            continue
+        flat = oracle.flatten(bl.elements)
+        frac, guarded = judge_quick(flat, ic, src, fm.draw_f32(src, seed, first, n, rng))
+        assert guarded > 0.99 and frac > 0.985

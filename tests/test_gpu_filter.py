@@ -180,24 +180,55 @@ def test_filter_on_equals_filter_off_at_scale(torch_cuda, cuda_lib, math):
     for bl, xdist, min_filtered in cases:
         src = eng.make_source(CeNTREXVelocityDistribution(), xdist)
         on, off = propagator(cuda_lib, bl.elements, 0, math), propagator(cuda_lib, bl.elements, 2, math)
+        slow = propagator(cuda_lib, bl.elements, 4, math)      # per-molecule tolerances only
         # Philox source
         a = on.propagate_philox(src, 99, 1 << 35, n, want_fate=True)
         fa, ca, wa = a.fate.clone(), a.counters.clone(), a.work.clone()
         b = off.propagate_philox(src, 99, 1 << 35, n, want_fate=True)
+        c = slow.propagate_philox(src, 99, 1 << 35, n, want_fate=True)
         torch.cuda.synchronize()
         assert torch.equal(fa, b.fate) and torch.equal(ca, b.counters)
-        assert torch.equal(wa[:5], b.work[:5])
-        assert int(wa[5]) >= min_filtered * n and int(b.work[5]) == 0
+        assert torch.equal(fa, c.fate) and torch.equal(ca, c.counters)
+        assert torch.equal(wa[:5], b.work[:5]) and torch.equal(wa[:5], c.work[:5])
+        assert int(wa[5]) >= (min_filtered - 0.01) * n and int(b.work[5]) == 0
+        assert int(c.work[5]) >= min_filtered * n and int(c.work[5]) >= int(wa[5])
         # replayed initial conditions
         ic = on.draw(src, 99, 1 << 35, n)
-        on.reset(), off.reset()
+        on.reset(), off.reset(), slow.reset()
         a = on.propagate_ic(ic, want_fate=True)
         b = off.propagate_ic(ic, want_fate=True)
+        c = slow.propagate_ic(ic, want_fate=True)
         torch.cuda.synchronize()
         assert torch.equal(a.fate, b.fate) and torch.equal(a.counters, b.counters)
+        assert torch.equal(a.fate, c.fate) and torch.equal(a.counters, c.counters)
         assert torch.equal(a.fate, fa)                     # and the same as the Philox run
-        assert torch.equal(a.work[:5], b.work[:5])
-        assert int(a.work[5]) >= min_filtered * n
+        assert torch.equal(a.work[:5], b.work[:5]) and torch.equal(a.work[:5], c.work[:5])
+        assert int(a.work[5]) >= (min_filtered - 0.005) * n
+
+
+@pytest.mark.parametrize("flags", [0, 4])
+def test_both_filter_forms_on_aimed_and_hostile_inputs(torch_cuda, cuda_lib, flags):
+    """The constant-threshold form (default) and the per-molecule-tolerance form (flag 4) separately."""
+    rng = np.random.default_rng(77 + flags)
+    base = standard_ics(64, 9, 3.0)
+    hostile = np.repeat(base, 10, axis=1)
+    k = np.arange(hostile.shape[1]) % 10
+    hostile[5, k == 1] = 0.0
+    hostile[5, k == 2] *= -1
+    hostile[0, k == 3] = np.nan
+    hostile[4, k == 4] = np.inf
+    hostile[5, k == 5] = 1e-300
+    hostile[0, k == 7] = 1e200
+    hostile[2, k == 8] = -3.0
+    hostile[5, k == 9] = 20.0
+    for bl in (lens_beamline(lens_table()), apertures_beamline(), spa_beamline()):
+        flat = oracle.flatten(bl.elements)
+        for ic in (fm.aimed_ics(flat, 200000, rng, 1e-6, standard_ics(200000, 19)),
+                   fm.aimed_ics(flat, 200000, rng, 1e-8, standard_ics(200000, 20)), hostile):
+            want = oracle.propagate(bl.elements, ic)
+            fate, counters, work, _ = fates_only(torch_cuda, propagator(cuda_lib, bl.elements, flags), ic)
+            np.testing.assert_array_equal(fate, want["fate"])
+            np.testing.assert_array_equal(work[:3], want["work"])
 
 
 def test_single_precision_source_against_the_model(torch_cuda, cuda_lib):
