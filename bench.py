@@ -243,11 +243,13 @@ def run_ours(args):
     barrier()
     lib.cmt_timing_enable(1)
     lib.cmt_timing_read(None, None, 1)
+    lib.cmt_launch_count(1)
     prop.reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         res = step()
+    launches = int(lib.cmt_launch_count(0))       # walk + lens segments + tail, per step; pass B replays the same launches
     merge_counter()
     e1.record()
     torch.cuda.synchronize()
@@ -257,14 +259,13 @@ def run_ours(args):
     n_k = (C.c_int64 * 4)()
     lib.cmt_timing_read(ms_k, n_k, 1)
     lib.cmt_timing_enable(0)
-    launches = int(n_k[0] + n_k[1])
 
     # ---- pass B (the headline value): the same K steps, consecutive steps on alternating streams so
     # that the lens integrator of one batch overlaps the walk kernel of the next ----
     slots = [None] * args.steps if args.no_overlap else [k % prop.n_slots for k in range(args.steps)]
     graphs = None
     if not args.no_overlap and not args.no_graphs:
-        # one CUDA graph per stream (header memset + walk + lens): a replay is a single host-side launch
+        # one CUDA graph per stream (header memset + walk + lens segments + tail): a replay is a single host-side launch
         graphs = [prop.capture_ic(ic, first_index=first, want_fate=True, slot=s) for s in range(prop.n_slots)]
 
         def step(slot=None, _plain=step):                      # noqa: F811
@@ -363,14 +364,14 @@ def run_ours(args):
     lens_tflops = flop_lens / (lens_ms * 1e-3) / 1e12 if lens_ms > 0 else None
     fp64_peak_tflops = 2 * dfma.value / 1e12       # FMA = 2 flop
     roofline = {
-        "kernel": "lens_kernel", "bound": "fp64", "achieved": lens_tflops, "peak": fp64_peak_tflops,
+        "kernel": "lens_seg_kernel (the lens stage of one step: 4 segment launches of 150 RK steps + tail_kernel)", "bound": "fp64", "achieved": lens_tflops, "peak": fp64_peak_tflops,
         "unit": "TFLOP/s", "frac": (lens_tflops / fp64_peak_tflops) if lens_tflops else None,
         "traffic": NCU_TRAFFIC_LENS_1E7 * n / 1e7, "traffic_source": "profiles/r01_full_e_round_end.txt (ncu --set full)",
         "fp64_pipe_utilisation_ncu": 0.650,
         "peak_source": "measured live: cmt_fp64_peak DFMA stream (no FP64 figure in MEASURED_PEAKS.json)",
         "algorithmic_flop_per_launch": flop_lens, "avg_launch_ms": lens_ms,
         "share_of_step": lens_ms / (ms_seq / args.steps) if ms_seq > 0 else None,
-        "timed_in": "pass A: the same K steps back to back on one stream (kernels not overlapped), CUDA events per launch",
+        "timed_in": "pass A: the same K steps back to back on one stream (kernels not overlapped), CUDA events around the lens stage of every step",
         "dadd_peak_tops": dadd.value / 1e12,
     }
     walk_gbs = BYTES_PER_MOLECULE * n / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else None
@@ -474,7 +475,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "value_one_stream": value_seq, "ms_per_step_one_stream": ms_seq / args.steps,
             "overlap": "none" if args.no_overlap else f"{prop.n_slots} streams: consecutive steps alternate streams (independent batches)"
-                       + ("" if graphs is None else "; each step replays a CUDA graph (memset + walk + lens)"),
+                       + ("" if graphs is None else "; each step replays a CUDA graph (memset + walk + lens segments + tail)"),
             "roofline": roofline, "roofline_walk": roofline_walk,
             "cpu_baseline": cpu,
             "clocks": clocks,
@@ -500,7 +501,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap", action="store_true", help="issue every step on one stream")
     ap.add_argument("--no-contracted", action="store_true", help="skip the contracted-arithmetic pass")
-    ap.add_argument("--slots", type=int, default=3, help="streams the overlapped steps alternate over")
+    ap.add_argument("--slots", type=int, default=4, help="streams the overlapped steps alternate over")
     ap.add_argument("--no-graphs", action="store_true", help="launch the overlapped steps individually instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -4,6 +4,7 @@
 // exact threshold/slope precomputation, launches, staging for the host-buffer
 // entry points.  No torch, no C++ types across the boundary.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -58,6 +59,20 @@ struct DeviceGuard {
 
 extern "C" const char *cmt_last_error(void) { return g_err; }
 
+static int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+// kernel launches issued by this library (bench.py reports them)
+static std::atomic<int64_t> g_launches{0};
+static inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" int64_t cmt_launch_count(int reset)
+{
+    return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
 static int g_debug_flags = 0;
 extern "C" int cmt_debug_flags(int flags)
 {
@@ -66,13 +81,6 @@ extern "C" int cmt_debug_flags(int flags)
     return old;
 }
 extern "C" int cmt_version(void) { return CMT_VERSION; }
-
-using LensFn = void (*)(const Params, int64_t, const cmt_outputs_t, Queue);
-static LensFn lens_variant(bool contract, bool mesh)
-{
-    if (contract) return mesh ? lens_kernel<true, true> : lens_kernel<true, false>;
-    return mesh ? lens_kernel<false, true> : lens_kernel<false, false>;
-}
 
 // ---------------------------------------------------------------------------
 // beamline handle
@@ -439,8 +447,12 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
         }
         P.tab = bl->d_tab;
         if (bl->tab_bytes > 40 * 1024) {
-            for (int v = 0; v < 4; ++v)
-                cudaFuncSetAttribute(lens_variant(v & 1, v >> 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            cudaFuncSetAttribute(lens_seg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            cudaFuncSetAttribute(lens_seg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            cudaFuncSetAttribute(tail_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            cudaFuncSetAttribute(tail_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            cudaFuncSetAttribute(tail_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            cudaFuncSetAttribute(tail_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
             cudaFuncSetAttribute(trajectory_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
             cudaFuncSetAttribute(trajectory_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
             cudaFuncSetAttribute(crossing_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
@@ -478,7 +490,10 @@ extern "C" size_t cmt_workspace_bytes(const cmt_beamline_t *bl, int64_t n_max)
 {
     if (!bl || n_max < 0) return 0;
     if (bl->P.first_lens >= bl->P.n_el) return WS_HEADER;
-    return WS_HEADER + (size_t)QUEUE_COMPONENTS * sizeof(double) * (size_t)n_max;
+    // two queue arrays that alternate between the lens segments: the walk kernel fills the first one with
+    // the survivors of the lens entrance test; molecules leave the lens only in the last segment, which has
+    // no successor, so the exit queue takes the array that segment would have written survivors to
+    return WS_HEADER + 2 * (size_t)QUEUE_COMPONENTS * sizeof(double) * (size_t)n_max;
 }
 
 // ---------------------------------------------------------------------------
@@ -570,6 +585,7 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
     if (rc) return rc;
     if (n < 0) return fail(CMT_EINVAL, "n < 0");
     if (n == 0) return CMT_OK;
+    if (n >= (1ll << SEG_INDEX_BITS)) return fail(CMT_EINVAL, "n must be below 2^%d per launch", SEG_INDEX_BITS);
     const bool has_lens = bl->P.first_lens < bl->P.n_el;
     const size_t need = cmt_workspace_bytes(bl, n);
     if (!workspace || workspace_bytes < need)
@@ -585,6 +601,12 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
     Q.cursor = Q.count + 1;
     Q.q = reinterpret_cast<double *>(static_cast<char *>(workspace) + WS_HEADER);
     Q.cap = has_lens ? n : 0;
+    // header words: [0],[1] entry queue (count, cursor); [2],[3] exit queue; [4+2k],[5+2k] output of lens segment k
+    Queue X;
+    X.count = Q.count + 2;
+    X.cursor = Q.count + 3;
+    X.q = nullptr;               // set with the segment count below
+    X.cap = Q.cap;
     CUDA_TRY(cudaMemsetAsync(workspace, 0, WS_HEADER, st));
 
     cmt_source_t S;
@@ -592,7 +614,12 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
     if (src) S = *src;
 
     const int64_t tiles = (n + WALK_THREADS - 1) / WALK_THREADS;
-    const int grid_walk = (int)std::min<int64_t>(tiles, (int64_t)bl->n_sm * (2048 / WALK_THREADS));
+    // Walk CTAs per SM: all thread slots for the Philox source (issue-bound), half of them when the initial
+    // conditions stream from HBM (measured: 0.162 -> 0.157 ms alone, overlapped step 0.433 -> 0.424 ms)
+    static const int tune_walk_ctas = env_int("CMT_TUNE_WALK_CTAS", 0);   // experiments only
+    static const int tune_lens_prio = env_int("CMT_TUNE_LENS_PRIO", 1);
+    const int walk_ctas = tune_walk_ctas > 0 ? tune_walk_ctas : (philox ? 2048 : 1024) / WALK_THREADS;
+    const int grid_walk = (int)std::min<int64_t>(tiles, (int64_t)bl->n_sm * walk_ctas);
     {
         ScopedTimer tm(0, st);
         // variants: source (replay / Philox) x arithmetic (exact / contracted) x Honeycomb test compiled in
@@ -604,25 +631,71 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
             {{walk_kernel<true, false, false>, walk_kernel<true, false, true>},
              {walk_kernel<true, true, false>, walk_kernel<true, true, true>}}};
         const bool contract = bl->math == CMT_MATH_CONTRACTED;
+        cudaLaunchConfig_t wcfg;
+        memset(&wcfg, 0, sizeof(wcfg));
+        wcfg.gridDim = dim3(grid_walk); wcfg.blockDim = dim3(WALK_THREADS);
+        wcfg.stream = st;
         if (philox && bl->P.filt.n > 0) {
             // the quick filter's thresholds depend on the source's error bounds: per launch, by value
             Params P = bl->P;
             build_quick(bl->planes, bl->P.g, &S, P.quick);
-            walk[1][contract][bl->has_mesh]<<<grid_walk, WALK_THREADS, 0, st>>>(P, S, seed, nullptr, 0, n, first_index, *out, Q);
+            CUDA_TRY(cudaLaunchKernelEx(&wcfg, walk[1][contract][bl->has_mesh], P, S, seed, (const double *)nullptr,
+                                        (int64_t)0, n, first_index, *out, Q));
         } else {
-            walk[philox][contract][bl->has_mesh]<<<grid_walk, WALK_THREADS, 0, st>>>(
-                bl->P, S, seed, philox ? nullptr : ic, philox ? 0 : ic_ld, n, first_index, *out, Q);
+            CUDA_TRY(cudaLaunchKernelEx(&wcfg, walk[philox][contract][bl->has_mesh], bl->P, S, seed,
+                                        philox ? (const double *)nullptr : ic, philox ? (int64_t)0 : ic_ld, n,
+                                        first_index, *out, Q));
         }
+        count_launch();
     }
     CUDA_TRY(cudaGetLastError());
     if (has_lens) {
-        // persistent lanes: enough CTAs to fill every SM, no more than the queue can feed
-        const int64_t max_ctas = (n + LENS_THREADS - 1) / LENS_THREADS;
-        const int ctas_per_sm = bl->math == CMT_MATH_CONTRACTED ? LENS_MIN_CTAS_CONTRACTED : LENS_MIN_CTAS;
-        const int grid_lens = (int)std::min<int64_t>(max_ctas, (int64_t)bl->n_sm * ctas_per_sm);
+        // Lens stage: the first lens' integrator as a chain of segment launches, then the elements behind
+        // it for the molecules that got through.  The integrator launches run at the highest stream
+        // priority: when steps overlap on several streams, their CTAs are placed ahead of the next
+        // step's walk CTAs, which fill what is left (measured: 0.549 -> 0.527 ms per step).
         ScopedTimer tm(1, st);
-        lens_variant(bl->math == CMT_MATH_CONTRACTED, bl->has_mesh)<<<grid_lens, LENS_THREADS, bl->tab_bytes, st>>>(
-            bl->P, first_index, *out, Q);
+        static const int tune_seg = env_int("CMT_TUNE_SEG", LENS_SEGMENT_STEPS);          // experiments only
+        static const int seg_per_sm = env_int("CMT_TUNE_SEG_CTAS", LENS_SEG_GRID_CTAS);   // experiments only
+        const bool contract = bl->math == CMT_MATH_CONTRACTED;
+        int least = 0, greatest = 0;
+        if (tune_lens_prio) cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributePriority;
+        attr.val.priority = tune_lens_prio ? greatest : 0;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.blockDim = dim3(LENS_THREADS);
+        cfg.dynamicSmemBytes = bl->tab_bytes; cfg.stream = st; cfg.attrs = &attr; cfg.numAttrs = 1;
+
+        const int n_steps = bl->P.el[bl->P.first_lens].n_steps;
+        constexpr int max_seg = (int)(WS_HEADER / 16) - 2;                          // a (count, cursor) pair per segment
+        int seg = std::max(1, tune_seg);
+        if (n_steps >= (1 << (63 - SEG_INDEX_BITS))) seg = n_steps;                 // the step count would not fit its bit field
+        else if ((n_steps + seg - 1) / seg > max_seg) seg = (n_steps + max_seg - 1) / max_seg;
+        const int n_seg = std::max(1, (n_steps + seg - 1) / seg);
+        const int64_t max_ctas = (n + LENS_THREADS - 1) / LENS_THREADS;
+        cfg.gridDim = dim3((unsigned)std::min<int64_t>(max_ctas, (int64_t)bl->n_sm * seg_per_sm));
+        X.q = Q.q + (size_t)(n_seg & 1) * QUEUE_COMPONENTS * (size_t)Q.cap;   // the last segment's unused output array
+        for (int k = 0; k < n_seg; ++k) {
+            Queue A, B;
+            A.cap = B.cap = Q.cap;
+            A.q = Q.q + (size_t)(k & 1) * QUEUE_COMPONENTS * (size_t)Q.cap;
+            B.q = Q.q + (size_t)((k + 1) & 1) * QUEUE_COMPONENTS * (size_t)Q.cap;
+            A.count = k == 0 ? Q.count : Q.count + 4 + 2 * (k - 1);
+            A.cursor = A.count + 1;
+            B.count = Q.count + 4 + 2 * k;
+            B.cursor = B.count + 1;
+            if (contract) CUDA_TRY(cudaLaunchKernelEx(&cfg, lens_seg_kernel<true>, bl->P, first_index, *out, A, B, X, seg));
+            else CUDA_TRY(cudaLaunchKernelEx(&cfg, lens_seg_kernel<false>, bl->P, first_index, *out, A, B, X, seg));
+            count_launch();
+        }
+        const int grid_tail = (int)std::min<int64_t>((n + TRAJ_THREADS - 1) / TRAJ_THREADS, (int64_t)bl->n_sm * 8);
+        using TailFn = void (*)(const Params, int64_t, const cmt_outputs_t, Queue);
+        static const TailFn tail[2][2] = {{tail_kernel<false, false>, tail_kernel<false, true>},
+                                          {tail_kernel<true, false>, tail_kernel<true, true>}};
+        tail[contract][bl->has_mesh]<<<grid_tail, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, first_index, *out, X);
+        count_launch();
     }
     CUDA_TRY(cudaGetLastError());
     return CMT_OK;
@@ -660,6 +733,7 @@ extern "C" int cmt_philox_draw(const cmt_source_t *src, uint64_t seed, int64_t f
     {
         ScopedTimer tm(3, st);
         draw_kernel<<<grid, 256, 0, st>>>(*src, seed, first_index, index, n, ic, ic_ld);
+        count_launch();
     }
     CUDA_TRY(cudaGetLastError());
     return CMT_OK;

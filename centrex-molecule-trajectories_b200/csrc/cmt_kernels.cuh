@@ -6,11 +6,12 @@
 //                 optional final row, optional saved-index append); survivors
 //                 are compacted (warp ballot + one atomic per warp) into the
 //                 lens queue.
-//   lens_kernel   persistent lanes pull survivors from the queue and run a
-//                 per-lane state machine: RK steps while inside a lens, whole
-//                 apertures otherwise, until the molecule dies or is detected;
-//                 an idle lane immediately pulls the next survivor, so warps
-//                 stay full while molecules die at different steps.
+//   lens_seg_kernel  one SEGMENT of the first lens' RK integration for every
+//                 molecule of its input queue; survivors are re-packed into full
+//                 warps through the next queue, molecules that complete the lens
+//                 go to the exit queue.  Launched ceil(n_steps / segment) times.
+//   tail_kernel   the elements behind the first lens for the molecules of the
+//                 exit queue, one per thread.
 //   trajectory_kernel  re-propagates selected molecules and writes every row.
 //   draw_kernel   materialises the source's samples.
 //
@@ -26,7 +27,6 @@ namespace cmt {
 constexpr int WALK_THREADS = 64;   // small CTAs fit next to resident lens CTAs of another stream (measured: 256 -> 64 gives +3 % overlapped)
 constexpr int LENS_THREADS = 128;
 constexpr int TRAJ_THREADS = 64;
-constexpr int LENS_BURST = 4;       // RK steps per state-machine turn
 constexpr int QUEUE_COMPONENTS = 8;  // x,y,z,vx,vy,vz,t + global index bits
 
 struct Queue {
@@ -258,128 +258,176 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
 }
 
 // ---------------------------------------------------------------------------
-// lens kernel: persistent lanes, per-lane state machine
+// lens segment kernel + tail kernel: the lens integrator as a chain of short launches.
+//
+// Molecules die inside the lens at different steps (38 % of those that enter the CeNTREX lens hit the
+// bore, after 164 of 600 steps on average), and the FP64 pipe charges a warp instruction the same
+// whether 32 or 3 of its lanes are alive.  So the 600 steps are cut into segments; one launch of
+// lens_seg_kernel advances every molecule of its input queue by one segment and appends the survivors
+// to the next queue, which packs them into full warps again (ping-pong between two arrays; 64 B per
+// molecule and segment against ~150 RK steps of ~190 FP64 instructions).  A molecule that hits the
+// bore retires on the spot ("Inside lens"); one that completes the lens takes its exit row and goes
+// to the exit queue, from which tail_kernel walks the elements behind the lens (a later lens
+// included, through do_lens), one molecule per thread.
+//
+// Queue entry: x, y, z, vx, vy, vz, t and one word holding the molecule's index within the launch
+// (low SEG_INDEX_BITS bits) and the RK steps already taken (high bits).  Everything else a lane needs
+// (reciprocal of vz, dt, z increment, x*x + y*y) is recomputed from the entry by the same operations.
 // ---------------------------------------------------------------------------
-#ifndef LENS_MIN_CTAS
-#define LENS_MIN_CTAS 4            // exact arithmetic: 122 registers; 5 or 6 CTAs/SM spill and measured slower
+constexpr int SEG_INDEX_BITS = 44;
+constexpr int LENS_SEGMENT_STEPS = 150;   // RK steps per launch (measured: 75..150 equal, 300 and 600 slower)
+constexpr int LENS_SEG_GRID_CTAS = 3;     // CTAs per SM one launch asks for: leaves room for the next step's walk CTAs
+#ifndef LENS_SEG_MIN_CTAS
+#define LENS_SEG_MIN_CTAS 5               // register budget: 96 per thread, nothing spilled inside the step loop
 #endif
-#ifndef LENS_MIN_CTAS_CONTRACTED
-#define LENS_MIN_CTAS_CONTRACTED 4
-#endif
-template <bool CONTRACT, bool MESH>
-__global__ void __launch_bounds__(LENS_THREADS, CONTRACT ? LENS_MIN_CTAS_CONTRACTED : LENS_MIN_CTAS)
-lens_kernel(const __grid_constant__ Params P, int64_t first_index,
-            const __grid_constant__ cmt_outputs_t O, Queue Q)
+
+template <bool CONTRACT>
+__global__ void __launch_bounds__(LENS_THREADS, LENS_SEG_MIN_CTAS)
+lens_seg_kernel(const __grid_constant__ Params P, int64_t first_index, const __grid_constant__ cmt_outputs_t O,
+                Queue A, Queue B, Queue X, int seg_steps)
 {
     extern __shared__ double4 smem_tab[];
     __shared__ BlockAcc acc;
-    const unsigned long long count = min(*Q.count, (unsigned long long)Q.cap);
-    // When the queue cannot fill every lane, only the first ceil(count/128) CTAs take part:
-    // consecutive CTAs land on different SMs, so the survivors spread evenly over the chip.
-    if ((unsigned long long)blockIdx.x * LENS_THREADS >= count) return;
+    const unsigned long long count = min(*A.count, (unsigned long long)A.cap);
+    const unsigned long long n_groups = (count + 31ull) / 32ull;      // one group = one full warp
+    // when the queue cannot occupy every warp, only the first ceil(n_groups / warps per CTA) CTAs take part
+    if ((unsigned long long)blockIdx.x * (LENS_THREADS / 32) >= n_groups) return;
     for (int i = threadIdx.x; i < P.tab_total; i += blockDim.x) smem_tab[i] = P.tab[i];
     block_acc_init(acc);
     const bool reference_math = (P.flags & CMT_FLAG_REFERENCE_MATH) != 0;
     const double r6 = rcp_refined(6.0);
+    const DevElement &E = P.el[P.first_lens];
+    const int n_steps = E.n_steps;
+    const double bore_T = E.p[0];
+    const Table tb = table_of(E, smem_tab);
+    const double r_last = tb.t[tb.n - 1].x;
     unsigned rows_total = 0, steps_total = 0, oob_total = 0, ref_total = 0;
 
-    Mol m;
-    m.x = m.y = m.z = m.vx = m.vy = m.t = m.ax = m.ay = 0.0; m.vz = 1.0; m.rvz = 1.0;
-    int64_t local = 0;
-    int e = 0;              // element being processed
-    int step = -1;          // >= 0: RK steps already taken inside lens e
-    int n_steps = 0;        // of lens e
-    double bore_T = 0.0;    // of lens e
-    double r_last = 0.0;    // last abscissa of its table (contracted mode)
-    double s_xy = 0.0;      // x*x + y*y of the current position while inside a lens (exact mode)
-    bool have = false;
-    bool drained = false;   // warp-uniform: the queue has nothing left
-    Table tb;
-    tb.t = smem_tab; tb.n = 2; tb.inv_h = 0.0; tb.inv_h_f = 0.f;
-    LensConsts lc;
-    lc.dt = 0.0; lc.zinc = 0.0;
-
     for (;;) {
-        // ---- refill idle lanes ----
-        const unsigned idle = __ballot_sync(0xffffffffu, !have);
-        if (idle) {
-            if (!drained) {
-                const int leader = __ffs(idle) - 1;
-                unsigned long long base = 0;
-                if ((int)lane_id() == leader) base = atomicAdd(Q.cursor, (unsigned long long)__popc(idle));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (!have) {
-                    const unsigned long long k = base + __popc(idle & ((1u << lane_id()) - 1u));
-                    if (k < count) {
-                        const double *q = Q.q + k;
-                        m.x = q[0 * Q.cap];  m.y = q[1 * Q.cap];  m.z = q[2 * Q.cap];
-                        m.vx = q[3 * Q.cap]; m.vy = q[4 * Q.cap]; m.vz = q[5 * Q.cap];
-                        const double t = q[6 * Q.cap];
-                        local = __double_as_longlong(q[7 * Q.cap]);
-                        mol_begin<CONTRACT>(m, P.g);
-                        m.t = t;
-                        e = P.first_lens;
-                        const DevElement &E = P.el[e];
-                        step = 0; n_steps = E.n_steps; bore_T = E.p[0];
-                        tb = table_of(E, smem_tab);
-                        r_last = tb.t[tb.n - 1].x;
-                        lc = lens_consts<CONTRACT>(E, m);
-                        s_xy = radius_sq(m.x, m.y);
-                        have = true;
-                    }
-                }
-                if (base + __popc(idle) >= count) drained = true;
-            }
-            if (__ballot_sync(0xffffffffu, have) == 0) break;
-        }
+        unsigned long long g = 0;
+        if (lane_id() == 0) g = atomicAdd(A.cursor, 1ull);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= n_groups) break;
+        const unsigned long long k = g * 32ull + lane_id();
+        const bool have = k < count;
 
-        // ---- advance every busy lane: up to LENS_BURST RK steps, or one aperture ----
-        int fate = -1;
+        Mol m;
+        m.x = m.y = m.z = m.vx = m.vy = 0.0; m.vz = 1.0;
+        double t = 0.0;
+        long long local = 0;
+        int step = 0;
         if (have) {
-            CountRowsT<CONTRACT, MESH> rec;
-            if (step >= 0) {
-#pragma unroll 1
-                for (int b = 0; b < LENS_BURST; ++b) {
-                    int oob = 0;
-                    if (CONTRACT) lens_step_contracted(tb, r_last, lc, m, P.g, oob);
-                    else lens_step(tb, lc, r6, m, s_xy, P.g, oob, reference_math);
-                    oob_total += oob & 0xffff;
-                    ref_total += oob >> 16;
-                    ++steps_total;
-                    ++step;
-                    if (CONTRACT ? outside_radius<CONTRACT>(m, bore_T) : (s_xy > bore_T)) { fate = P.el[e].fate2; break; }   // "Inside lens"
-                    if (step >= n_steps) {
-                        lens_exit(P.el[e], m, P.g, rec);
-                        step = -1;
-                        ++e;
-                        break;
-                    }
-                }
-            } else if (e >= P.n_el) {
-                fate = P.fate_detected;
-            } else {
-                const DevElement &E = P.el[e];
-                if (E.type == CMT_LENS) {
-                    to_plane(m, E.z0, P.g, rec);
-                    if (outside_radius<CONTRACT>(m, E.p[0])) fate = E.fate;       // "Lens entrance"
-                    else {
-                        step = 0; n_steps = E.n_steps; bore_T = E.p[0];
-                        tb = table_of(E, smem_tab);
-                        r_last = tb.t[tb.n - 1].x;
-                        lc = lens_consts<CONTRACT>(E, m);
-                        s_xy = radius_sq(m.x, m.y);
-                        if (E.n_steps <= 0) { lens_exit(E, m, P.g, rec); step = -1; ++e; }
-                    }
-                } else {
-                    fate = do_aperture(E, m, P.g, rec);
-                    ++e;
-                }
-            }
-            rows_total += rec.n;
+            const double *q = A.q + k;
+            m.x = q[0 * A.cap];  m.y = q[1 * A.cap];  m.z = q[2 * A.cap];
+            m.vx = q[3 * A.cap]; m.vy = q[4 * A.cap]; m.vz = q[5 * A.cap];
+            t = q[6 * A.cap];
+            const long long w = __double_as_longlong(q[7 * A.cap]);
+            local = w & ((1ll << SEG_INDEX_BITS) - 1);
+            step = (int)(w >> SEG_INDEX_BITS);
         }
-        const bool done = have && fate >= 0;
-        retire(done, fate, m, local, first_index + local, acc, O);
-        if (done) have = false;
+        mol_begin<CONTRACT>(m, P.g);
+        m.t = t;
+        const LensConsts lc = lens_consts<CONTRACT>(E, m);
+        double s_xy = radius_sq(m.x, m.y);
+        const int end_step = min(n_steps, step + seg_steps);
+
+        bool dead = false;
+        if (have) {
+#pragma unroll 1
+            while (step < end_step) {
+                int oob = 0;
+                if (CONTRACT) lens_step_contracted(tb, r_last, lc, m, P.g, oob);
+                else lens_step(tb, lc, r6, m, s_xy, P.g, oob, reference_math);
+                oob_total += oob & 0xffff;
+                ref_total += oob >> 16;
+                ++steps_total;
+                ++step;
+                if (CONTRACT ? outside_radius<CONTRACT>(m, bore_T) : (s_xy > bore_T)) { dead = true; break; }   // "Inside lens"
+            }
+        }
+        const bool out = have && !dead && step >= n_steps;
+        const bool next = have && !dead && !out;
+
+        // through the lens: exit row, then the exit queue
+        if (__ballot_sync(0xffffffffu, out)) {
+            if (out) {
+                CountRowsT<CONTRACT, false> rec;
+                lens_exit(E, m, P.g, rec);
+                rows_total += rec.n;
+            }
+            const long long xpos = warp_append(out, X.count);
+            if (out && xpos < X.cap) {
+                double *x = X.q + xpos;
+                x[0 * X.cap] = m.x;  x[1 * X.cap] = m.y;  x[2 * X.cap] = m.z;
+                x[3 * X.cap] = m.vx; x[4 * X.cap] = m.vy; x[5 * X.cap] = m.vz;
+                x[6 * X.cap] = m.t;
+                x[7 * X.cap] = __longlong_as_double(local);
+            }
+        }
+        // still inside: next segment's queue
+        if (__ballot_sync(0xffffffffu, next)) {
+            const long long bpos = warp_append(next, B.count);
+            if (next && bpos < B.cap) {
+                double *q = B.q + bpos;
+                q[0 * B.cap] = m.x;  q[1 * B.cap] = m.y;  q[2 * B.cap] = m.z;
+                q[3 * B.cap] = m.vx; q[4 * B.cap] = m.vy; q[5 * B.cap] = m.vz;
+                q[6 * B.cap] = m.t;
+                q[7 * B.cap] = __longlong_as_double(local | ((long long)step << SEG_INDEX_BITS));
+            }
+        }
+        retire(dead, E.fate2, m, local, first_index + local, acc, O);
+    }
+    warp_add_work(acc, 0, rows_total);
+    warp_add_work(acc, 1, steps_total);
+    warp_add_work(acc, 2, oob_total);
+    warp_add_work(acc, 4, ref_total);
+    block_acc_flush(acc, P, O);
+}
+
+template <bool CONTRACT, bool MESH>
+__global__ void __launch_bounds__(TRAJ_THREADS)
+tail_kernel(const __grid_constant__ Params P, int64_t first_index, const __grid_constant__ cmt_outputs_t O, Queue X)
+{
+    extern __shared__ double4 smem_tab[];
+    __shared__ BlockAcc acc;
+    const unsigned long long count = min(*X.count, (unsigned long long)X.cap);
+    if ((unsigned long long)blockIdx.x * TRAJ_THREADS >= count) return;
+    for (int i = threadIdx.x; i < P.tab_total; i += blockDim.x) smem_tab[i] = P.tab[i];
+    block_acc_init(acc);
+    unsigned rows_total = 0, steps_total = 0, oob_total = 0, ref_total = 0;
+    for (unsigned long long k0 = (unsigned long long)blockIdx.x * TRAJ_THREADS; k0 < count;
+         k0 += (unsigned long long)gridDim.x * TRAJ_THREADS) {
+        const unsigned long long k = k0 + threadIdx.x;
+        const bool valid = k < count;
+        Mol m;
+        m.x = m.y = m.z = m.vx = m.vy = 0.0; m.vz = 1.0;
+        int64_t local = 0;
+        double t = 0.0;
+        if (valid) {
+            const double *x = X.q + k;
+            m.x = x[0 * X.cap];  m.y = x[1 * X.cap];  m.z = x[2 * X.cap];
+            m.vx = x[3 * X.cap]; m.vy = x[4 * X.cap]; m.vz = x[5 * X.cap];
+            t = x[6 * X.cap];
+            local = __double_as_longlong(x[7 * X.cap]);
+        }
+        mol_begin<CONTRACT>(m, P.g);
+        m.t = t;
+        int fate = -1;
+        if (valid) {
+            CountRowsT<CONTRACT, MESH> rec;
+            int steps = 0, oob = 0;
+            for (int e = P.first_lens + 1; e < P.n_el && fate < 0; ++e) {
+                const DevElement &E = P.el[e];
+                if (E.type == CMT_LENS) fate = do_lens(P, E, smem_tab, m, rec, steps, oob);
+                else fate = do_aperture(E, m, P.g, rec);
+            }
+            if (fate < 0) fate = P.fate_detected;
+            rows_total += rec.n - steps;          // do_lens records a row per RK step; the work counter keeps them apart
+            steps_total += steps;
+            oob_total += oob & 0xffff;
+            ref_total += oob >> 16;
+        }
+        retire(valid, fate, m, local, first_index + local, acc, O);
     }
     warp_add_work(acc, 0, rows_total);
     warp_add_work(acc, 1, steps_total);

@@ -90,6 +90,7 @@ _SIGNATURES = {
                                       C.c_void_p, C.c_void_p]),
     "cmt_timing_enable": (C.c_int, [C.c_int]),
     "cmt_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
+    "cmt_launch_count": (C.c_int64, [C.c_int]),
     "cmt_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cmt_selftest": (C.c_int, [C.c_int, C.c_int64, C.c_uint64, C.c_int, C.POINTER(C.c_int64)]),
     "cmt_debug_flags": (C.c_int, [C.c_int]),

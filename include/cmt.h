@@ -148,7 +148,9 @@ int cmt_beamline_set_math(cmt_beamline_t *bl, int mode);
 int cmt_beamline_max_rows(const cmt_beamline_t *bl);
 int cmt_beamline_device(const cmt_beamline_t *bl);
 
-/* Bytes of device scratch a propagation call over up to n_max molecules needs. */
+/* Bytes of device scratch a propagation call over up to n_max molecules needs: a 256-byte header of
+ * counters and, for a beamline with a lens, two queue arrays of 64 B per molecule (worst case: every
+ * molecule enters the lens); only the part that is used is ever touched. */
 size_t cmt_workspace_bytes(const cmt_beamline_t *bl, int64_t n_max);
 
 /* ---- the hot path ------------------------------------------------------ */
@@ -223,10 +225,15 @@ int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t *src, uint6
 /* Per-kernel device time of the calls made on this thread since the last
  * reset, measured with CUDA events on the launch stream (enable first).
  * ms[0] = walk kernel (ballistic + aperture tests up to the first lens),
- * ms[1] = lens kernel (RK integrator + downstream elements), ms[2] = trajectory
- * kernel, ms[3] = source-only kernel; launches[k] = number of launches. */
+ * ms[1] = lens stage (the segment launches of the RK integrator + the tail kernel for the
+ * elements behind the lens, timed as one interval per propagation call), ms[2] = trajectory
+ * kernel, ms[3] = source-only kernel; launches[k] = number of timed intervals. */
 int cmt_timing_enable(int on);
 int cmt_timing_read(double ms[4], int64_t launches[4], int reset);
+
+/* Kernel launches this library has issued in the process so far (walk, lens segments, tail, source);
+ * reset != 0 also sets the count back to zero. */
+int64_t cmt_launch_count(int reset);
 
 /* Measured FP64 pipe ceilings on `device` (dependent-chain-free DFMA / DADD
  * streams), in operations per second; used as roofline denominators. */

@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """One bench step of configs[1] (1e7 molecules, lens beamline) in each source mode, for ncu:
 
-    ncu --set full --clock-control none --import-source on -k regex:'walk_kernel|lens_kernel' -s 4 -c 4 \
-        -o gpurun_out/prof python profiles/prof_step.py
+    ncu --set full --clock-control none --import-source on -k regex:'walk_kernel|lens_seg_kernel|tail_kernel' \
+        -s 12 -c 12 -o gpurun_out/prof python profiles/prof_step.py
 
-launches: [warm-up] walk<ic>, lens, walk<philox>, lens, then the same four again (captured)."""
+launches: [warm-up] walk<ic>, 4 x lens_seg, tail, walk<philox>, 4 x lens_seg, tail, then the same twelve
+again (captured)."""
 import sys
 from pathlib import Path
 
