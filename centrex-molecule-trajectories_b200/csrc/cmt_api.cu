@@ -222,6 +222,8 @@ static void build_quick(const std::vector<PlaneD> &planes, double g, const cmt_s
     Q.pos_g = float_down(pos_g); Q.z0_g = float_down(z0_g); Q.ainv_g = float_down(ainv_g); Q.ang_g = float_down(ang_g);
     Q.eva_g = float_down(eva_g); Q.relvz_g = float_down(relvz_g); Q.ex_g = float_down(ex_g);
     Q.usable = 1;
+    Q.all_circles = 1;
+    for (const PlaneD &p : planes) if (p.kind != CMT_FILTER_CIRCLE) Q.all_circles = 0;
 }
 
 extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements, const cmt_table_t *tables,
