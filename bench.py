@@ -45,9 +45,9 @@ UNIT = "molecules/s"
 WORKLOAD = ("configs[1]: examples/lens_simulation_beamline.py full CeNTREX beamline with ElectrostaticLens, "
             "J=2 mJ=0 Stark curve at 27.6 kV, CeNTREX velocity/position distributions")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload at
-# 1e7 molecules (profiles/r01_full_e_round_end.txt); scaled linearly when --molecules differs
-NCU_TRAFFIC_LENS_1E7 = 3.52e6
-NCU_TRAFFIC_WALK_1E7 = 481.3e6 + 17.8e6
+# 1e7 molecules (profiles/r01_full_f_segments.txt); scaled linearly when --molecules differs
+NCU_TRAFFIC_LENS_1E7 = 13.2e6            # four segment launches + tail: 3.52 + 2.78 + 2.42 + 2.25 + 2.21 MB read
+NCU_TRAFFIC_WALK_1E7 = 516.8e6 + 12.3e6
 # algorithmic work per unit
 FLOP_PER_ROW = 30      # one ballistic step + hit test
 FLOP_PER_STEP = 162    # one lens RK step (4 force evaluations)
@@ -366,8 +366,9 @@ def run_ours(args):
     roofline = {
         "kernel": "lens_seg_kernel (the lens stage of one step: 4 segment launches of 150 RK steps + tail_kernel)", "bound": "fp64", "achieved": lens_tflops, "peak": fp64_peak_tflops,
         "unit": "TFLOP/s", "frac": (lens_tflops / fp64_peak_tflops) if lens_tflops else None,
-        "traffic": NCU_TRAFFIC_LENS_1E7 * n / 1e7, "traffic_source": "profiles/r01_full_e_round_end.txt (ncu --set full)",
-        "fp64_pipe_utilisation_ncu": 0.650,
+        "traffic": NCU_TRAFFIC_LENS_1E7 * n / 1e7, "traffic_source": "profiles/r01_full_f_segments.txt (ncu --set full, summed over the stage's launches)",
+        "fp64_pipe_utilisation_ncu": {"segment_1": 0.631, "segment_2": 0.586, "segment_3": 0.552, "segment_4": 0.525,
+                                      "at_8e7_molecules_per_launch": 0.695},
         "peak_source": "measured live: cmt_fp64_peak DFMA stream (no FP64 figure in MEASURED_PEAKS.json)",
         "algorithmic_flop_per_launch": flop_lens, "avg_launch_ms": lens_ms,
         "share_of_step": lens_ms / (ms_seq / args.steps) if ms_seq > 0 else None,
@@ -378,7 +379,7 @@ def run_ours(args):
     roofline_walk = {
         "kernel": "walk_kernel<ic>", "bound": "hbm", "achieved": walk_gbs, "peak": hbm_peak, "unit": "GB/s",
         "frac": (walk_gbs / hbm_peak) if walk_gbs else None, "traffic": NCU_TRAFFIC_WALK_1E7 * n / 1e7,
-        "traffic_source": "profiles/r01_full_e_round_end.txt (ncu --set full)", "peak_source": hbm_src,
+        "traffic_source": "profiles/r01_full_f_segments.txt (ncu --set full)", "peak_source": hbm_src,
         "algorithmic_bytes_per_launch": BYTES_PER_MOLECULE * n, "avg_launch_ms": walk_ms,
         "share_of_step": walk_ms / (ms_seq / args.steps) if ms_seq > 0 else None,
         "algorithmic_flop_per_launch": flop_rows,

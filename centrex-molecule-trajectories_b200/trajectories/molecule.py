@@ -19,7 +19,7 @@ _DEFAULT_A = np.array((0, -g, 0))
 class Trajectory:
     """Row store: one row per recorded point, `n` rows in use."""
 
-    __slots__ = ("x", "v", "a", "t", "n")
+    __slots__ = ("x", "v", "a", "t", "n", "_rows")
 
     def __init__(self, beamline=None, n_rows: int = None):
         if n_rows is None:
@@ -37,9 +37,22 @@ class Trajectory:
     def from_rows(cls, rows: np.ndarray) -> "Trajectory":
         """Zero-copy view of a row block [n,10]."""
         tr = object.__new__(cls)
-        tr.x, tr.v, tr.a, tr.t = rows[:, 0:3], rows[:, 3:6], rows[:, 6:9], rows[:, 9]
+        tr._rows = rows          # x, v, a, t are sliced out of it on first access (__getattr__)
         tr.n = rows.shape[0]
         return tr
+
+    def __getattr__(self, name):
+        # Only reached while a slot is unset: a trajectory wrapped by from_rows materialises its four
+        # views the first time one of them is asked for (a run that returns thousands of molecules
+        # otherwise spends more time slicing than propagating); afterwards they are plain attributes.
+        if name in ("x", "v", "a", "t"):
+            try:
+                rows = object.__getattribute__(self, "_rows")
+            except AttributeError:
+                raise AttributeError(name) from None
+            self.x, self.v, self.a, self.t = rows[:, 0:3], rows[:, 3:6], rows[:, 6:9], rows[:, 9]
+            return object.__getattribute__(self, name)
+        raise AttributeError(name)
 
     def as_rows(self) -> np.ndarray:
         """The used rows as one [n,10] block."""
@@ -98,9 +111,11 @@ class Molecule:
     @classmethod
     def from_rows(cls, rows: np.ndarray, aperture_hit: str, alive: bool) -> "Molecule":
         """Wrap GPU-produced rows [n,10]."""
-        mol = cls(alive=alive)
-        mol.trajectory = Trajectory.from_rows(rows)
-        mol.aperture_hit = aperture_hit
+        tr = object.__new__(Trajectory)
+        tr._rows = rows
+        tr.n = rows.shape[0]
+        mol = object.__new__(cls)      # same state as cls(alive=alive) followed by the two assignments
+        mol.__dict__ = {"alive": alive, "trajectory": tr, "aperture_hit": aperture_hit}
         return mol
 
     # -- state of the last recorded point --------------------------------------

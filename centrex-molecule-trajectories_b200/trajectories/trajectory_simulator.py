@@ -327,9 +327,8 @@ class TrajectorySimulator:
     def _collect(prop: "eng.Propagator", ic, select=None) -> List[Molecule]:
         rows, offsets, fate = prop.trajectories(ic, select=select)
         names = prop.flat.fate_names
-        out = []
-        for k in range(len(fate)):
-            name = names[int(fate[k])]
-            # each trajectory is a view of its slice of the result block
-            out.append(Molecule.from_rows(rows[offsets[k]:offsets[k + 1]], name, alive=(name == "Detected")))
-        return out
+        from_rows = Molecule.from_rows
+        lo = np.asarray(offsets).tolist()
+        # each trajectory is a view of its slice of the result block
+        return [from_rows(rows[lo[k]:lo[k + 1]], names[f], names[f] == "Detected")
+                for k, f in enumerate(np.asarray(fate).tolist())]
