@@ -489,6 +489,29 @@ def test_unusual_beamlines(torch_cuda):
     np.testing.assert_array_equal(got["fin"][0:6], ic[:, :1000])
 
 
+@pytest.mark.parametrize("n_steps", [1, 149, 150, 151, 301, 2100, 2101, 3000])
+def test_lens_segment_boundaries(torch_cuda, n_steps):
+    """The lens integrator runs as launches of 150 RK steps (at most 14 launches: longer lenses get longer
+    segments); step counts on, next to and far beyond the segment boundaries, with elements behind the lens."""
+    from trajectories.beamline import Beamline
+    from trajectories.beamline_elements.apertures import CircularAperture, FieldPlates
+    from trajectories.beamline_elements.electrostatic_lens import ElectrostaticLens, make_interpolator
+
+    L = 0.6
+    lens = ElectrostaticLens(name="L", z0=0.4, L=L, dz=L / n_steps, a_interp=make_interpolator(*lens_table()))
+    assert lens.N_steps() == n_steps + 1                      # its rows: one per RK step and the exit row
+    bl = Beamline([CircularAperture(name="in", z0=0.05, L=0.01, d=0.03), lens,
+                   FieldPlates(name="fp", z0=1.1, L=0.2, w=0.03), CircularAperture(name="out", z0=1.5, L=0.01, d=0.02)])
+    ic = standard_ics(6000, 40 + n_steps % 7, 2.5)
+    want = oracle.propagate(bl.elements, ic)
+    got = gpu_propagate(torch_cuda, bl, ic)
+    assert want["work"][1] > 1000 * min(n_steps, 50)          # the lens is actually exercised
+    np.testing.assert_array_equal(got["fate"], want["fate"])
+    np.testing.assert_array_equal(got["counters"], want["counters"])
+    np.testing.assert_array_equal(got["work"][:3], want["work"])
+    assert relerr(got["fin"], want["fin"]) < TIGHT
+
+
 def test_table_out_of_range_is_counted_and_raised(torch_cuda):
     """A force evaluation beyond the a_interp table: the reference's interp1d raises ValueError
     (electrostatic_lens.py:209,217); here it is counted on the device and raised after the run."""
