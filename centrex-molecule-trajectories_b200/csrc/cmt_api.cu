@@ -616,11 +616,11 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
     if (src) S = *src;
 
     const int64_t tiles = (n + WALK_THREADS - 1) / WALK_THREADS;
-    // Walk CTAs per SM: all thread slots for the Philox source (issue-bound), half of them when the initial
-    // conditions stream from HBM (measured: 0.162 -> 0.157 ms alone, overlapped step 0.433 -> 0.424 ms)
+    // Walk CTAs per SM: all thread slots for the Philox source (issue-bound); 14 when the initial conditions
+    // stream from HBM (72 registers with the next tile's loads in flight: 14 CTAs of 64 threads are resident)
     static const int tune_walk_ctas = env_int("CMT_TUNE_WALK_CTAS", 0);   // experiments only
     static const int tune_lens_prio = env_int("CMT_TUNE_LENS_PRIO", 1);
-    const int walk_ctas = tune_walk_ctas > 0 ? tune_walk_ctas : (philox ? 2048 : 1024) / WALK_THREADS;
+    const int walk_ctas = tune_walk_ctas > 0 ? tune_walk_ctas : (philox ? 2048 : 896) / WALK_THREADS;
     const int grid_walk = (int)std::min<int64_t>(tiles, (int64_t)bl->n_sm * walk_ctas);
     {
         ScopedTimer tm(0, st);

@@ -203,6 +203,17 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
     // binary64 (a single call site of walk_exact keeps the kernel small).  Everything that steers
     // the loop is warp-uniform.
     int64_t tile = blockIdx.x;
+    // Replay mode: the initial conditions of the NEXT tile are requested before the current tile is
+    // judged, so that the HBM latency overlaps the filter instead of stalling the warp at each tile.
+    double pre[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    auto prefetch = [&](int64_t t) {
+        const int64_t i = t * WALK_THREADS + threadIdx.x;
+        if (t < n_tiles && i < n) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) pre[c] = ic[c * ic_ld + i];
+        }
+    };
+    if (!PHILOX && filt) prefetch(tile);
     for (;;) {
         int64_t j = 0;
         bool act = false;
@@ -218,11 +229,13 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
             tile += gridDim.x;
             if (filt) {
                 int fate = -1, rows = 0;
+                FiltIn q;
+                if (!PHILOX) {
+                    q = filter_input(pre[0], pre[1], pre[2], pre[3], pre[4], pre[5]);
+                    prefetch(tile);
+                }
                 if (valid) {
-                    FiltIn q;
                     if (PHILOX) q = draw_f32(S, seed, (uint64_t)(first_index + i));
-                    else q = filter_input(ic[0 * ic_ld + i], ic[1 * ic_ld + i], ic[2 * ic_ld + i],
-                                          ic[3 * ic_ld + i], ic[4 * ic_ld + i], ic[5 * ic_ld + i]);
                     fate = quick ? quick_fate(P.filt, P.quick, P.fate_detected, q, rows)
                                  : filter_fate(P.filt, P.fate_detected, q, rows);
                 }
