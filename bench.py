@@ -47,7 +47,7 @@ WORKLOAD = ("configs[1]: examples/lens_simulation_beamline.py full CeNTREX beaml
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload at
 # 1e7 molecules (profiles/r01_full_f_segments.txt); scaled linearly when --molecules differs
 NCU_TRAFFIC_LENS_1E7 = 13.2e6            # four segment launches + tail: 3.52 + 2.78 + 2.42 + 2.25 + 2.21 MB read
-NCU_TRAFFIC_WALK_1E7 = 516.8e6 + 12.3e6
+NCU_TRAFFIC_WALK_1E7 = 514.4e6 + 12.9e6
 # algorithmic work per unit
 FLOP_PER_ROW = 30      # one ballistic step + hit test
 FLOP_PER_STEP = 162    # one lens RK step (4 force evaluations)
