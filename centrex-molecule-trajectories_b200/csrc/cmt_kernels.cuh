@@ -31,7 +31,7 @@ constexpr int QUEUE_COMPONENTS = 8;  // x,y,z,vx,vy,vz,t + global index bits
 
 struct Queue {
     unsigned long long *count;   // survivors appended by walk_kernel
-    unsigned long long *cursor;  // next survivor to hand out in lens_kernel
+    unsigned long long *cursor;  // next group of 32 entries to hand out in lens_seg_kernel
     double *q;                   // [QUEUE_COMPONENTS][cap]
     int64_t cap;
 };

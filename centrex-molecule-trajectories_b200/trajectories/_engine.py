@@ -370,7 +370,7 @@ class Propagator:
         return PropagateResult(self.counters, self.work, fate, final, saved, self.flat.fate_names)
 
     def capture_ic(self, ic, first_index=0, want_fate=True, slot=0) -> "GraphedStep":
-        """Capture one propagate_ic call (header memset + walk + lens kernels) into a CUDA graph on
+        """Capture one propagate_ic call (header memset + walk + lens segment + tail kernels) into a CUDA graph on
         the slot's stream.  Replaying it costs one graph launch on the host instead of three
         launches plus the Python call path, which matters when a step lasts well under a
         millisecond and several processes share the host cores."""

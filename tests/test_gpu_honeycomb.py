@@ -93,7 +93,7 @@ def test_honeycomb_hostile_inputs(torch_cuda):
 
 
 def test_honeycomb_with_a_lens(torch_cuda):
-    """Honeycomb before the lens (walk kernel, generic element loop) and after it (lens kernel's downstream elements)."""
+    """Honeycomb before the lens (walk kernel, generic element loop) and after it (tail kernel)."""
     from trajectories.beamline import Beamline
     from trajectories.beamline_elements import Honeycomb
 
