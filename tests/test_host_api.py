@@ -266,6 +266,38 @@ def test_molecule_and_trajectory_containers():
     assert tr.n == 4 and tr.t[3] == 29
 
 
+def test_wrapped_trajectories_materialise_their_views_lazily():
+    """Molecule.from_rows keeps the row block and slices x, v, a, t out of it on first access; afterwards
+    they are plain attributes, as in the reference (molecule.py:115-131), whatever is done first."""
+    import copy
+    import pickle
+
+    from trajectories.molecule import Molecule
+
+    rows = np.arange(40, dtype=float).reshape(4, 10)
+
+    def fresh():
+        return Molecule.from_rows(rows.copy(), "Detected", True)
+
+    m = fresh()
+    assert m == Molecule(alive=True) and m.aperture_hit == "Detected" and m.trajectory.n == 4
+    assert m.trajectory.t.shape == (4,) and m.trajectory.a.shape == (4, 3)           # any of the four first
+    assert m.trajectory.x.base is not None                                            # views, not copies
+    np.testing.assert_array_equal(fresh().v(), rows[3, 3:6])
+    np.testing.assert_array_equal(fresh().trajectory.as_rows()[:, :9], rows[:, :9])
+    for clone in (pickle.loads(pickle.dumps(fresh())), copy.deepcopy(fresh())):
+        np.testing.assert_array_equal(clone.trajectory.x, rows[:, 0:3])
+        assert clone.alive and clone.aperture_hit == "Detected"
+    m = fresh()
+    m.update_trajectory(0.5)                                                          # grows the arrays, appends a row
+    assert m.trajectory.n == 5 and m.t() == rows[3, 9] + 0.5
+    m = fresh()
+    m.trajectory.drop_nans()
+    assert m.trajectory.x.shape == (4, 3)
+    with pytest.raises(AttributeError):
+        fresh().trajectory.nonexistent
+
+
 def test_distributions_draw_shapes_and_aliases():
     from trajectories import distributions as D
 
