@@ -934,10 +934,14 @@ extern "C" int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t 
     DeviceGuard guard(bl->device);
     CUDA_TRY(guard.status);
     HostPipe &p = g_pipe;
-    // one launch pair per 2^26 molecules (4.3 GB of queue workspace per stream): splitting a run
-    // further was measured slower (the lens integrator of a small chunk cannot keep its lanes
-    // refilled); consecutive chunks alternate streams
+    // One chunk per 2^26 molecules (8.6 GB of queue workspace per stream), consecutive chunks on
+    // alternating streams.  A run that fits one chunk is cut in two halves, one per stream, so that the
+    // walk kernel of the second half overlaps the lens segments of the first (1e7 molecules: 1.32e10 ->
+    // 1.40e10 molecules/s); three or more pieces were measured slower (the segments are latency-bound,
+    // 128 us each whatever their load).  Results do not depend on the cut: the source is indexed by the
+    // global molecule number.
     int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 26);
+    if (n <= chunk && n >= ((int64_t)1 << 21)) chunk = (n + 1) / 2;
     if (const char *env = getenv("CMT_PHILOX_CHUNK")) {          // experiments only
         const long long v = atoll(env);
         if (v > 0) chunk = std::min<int64_t>(n, (int64_t)v);

@@ -170,6 +170,10 @@ class TrajectorySimulator:
                     seed = int(s.item())
             lo, hi = eng.shard_range(total, rank, world)
             chunk = self.chunk
+            if not save_mask and (1 << 21) <= hi - lo <= chunk:
+                # a run that fits one chunk goes out as two halves on two streams: the walk kernel of the
+                # second overlaps the lens segments of the first (the result does not depend on the cut)
+                chunk = (hi - lo + 1) // 2
             for k, first in enumerate(range(lo, hi, chunk)):
                 n = min(chunk, hi - first)
                 if not save_mask:
