@@ -226,6 +226,27 @@ static void build_quick(const std::vector<PlaneD> &planes, double g, const cmt_s
     for (const PlaneD &p : planes) if (p.kind != CMT_FILTER_CIRCLE) Q.all_circles = 0;
 }
 
+// May the straight-line force evaluation (cmt_device.cuh: lens_acc_fast) be used with this table?  Its validity
+// record relies on: every knot, value and slope at most 2^400 in magnitude (no quotient overflows, no divisor
+// reaches 2^1017); knots non-negative; and every interval width r_{j+1} - r_j and every difference r - r_j for r in
+// [r_j, r_{j+1}) exact in binary64, which holds when r_{j+1} <= 2 r_j (Sterbenz) or r_j = 0.  The evenly spaced
+// tables the reference builds (linspace from 0) qualify; any other table is evaluated on the reference path.
+static bool table_fast_ok(const cmt_table_t &tb)
+{
+    const double big = std::ldexp(1.0, 400);
+    for (int i = 0; i < tb.n; ++i) {
+        if (!(tb.r[i] >= 0.0) || !(tb.r[i] <= big) || !(std::fabs(tb.a[i]) <= big)) return false;
+        if (i + 1 < tb.n) {
+            if (!(tb.r[i] == 0.0 || tb.r[i + 1] <= 2.0 * tb.r[i])) return false;
+            volatile double num = tb.a[i + 1] - tb.a[i];
+            volatile double den = tb.r[i + 1] - tb.r[i];
+            const double slope = num / den;
+            if (!(std::fabs(slope) <= big)) return false;
+        }
+    }
+    return true;
+}
+
 extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements, const cmt_table_t *tables,
                                    int n_tables, int n_fates, int fate_detected, double g, int device,
                                    cmt_beamline_t **out)
@@ -313,6 +334,7 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
             d.p[0] = radius_threshold(s.R);
             d.p[1] = s.dz;
             d.p[2] = (tb.n - 1) / (tb.r[tb.n - 1] - tb.r[0]);
+            d.p[3] = table_fast_ok(tb) ? 1.0 : 0.0;
             d.tab_off = tab_off[s.table];
             d.tab_len = tb.n;
             bl->max_rows += 2 + s.n_steps;
@@ -432,7 +454,7 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
                     // np.interp: slope = (fp[j+1]-fp[j]) / (xp[j+1]-xp[j]); same IEEE ops here
                     volatile double num = tb.a[i + 1] - tb.a[i];
                     volatile double den = tb.r[i + 1] - tb.r[i];
-                    e.y = tb.r[i + 1];
+                    e.y = den;                 // interval width (exact for tables that pass table_fast_ok)
                     e.w = num / den;
                 }
             }

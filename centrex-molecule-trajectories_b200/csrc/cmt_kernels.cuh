@@ -289,6 +289,10 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
 // ---------------------------------------------------------------------------
 constexpr int SEG_INDEX_BITS = 44;
 constexpr int LENS_SEGMENT_STEPS = 150;   // RK steps per launch (measured: 75..150 equal, 300 and 600 slower)
+#ifndef CMT_LENS_UNROLL
+#define CMT_LENS_UNROLL 1
+#endif
+constexpr int LENS_UNROLL = CMT_LENS_UNROLL;   // RK steps per trip of the segment loop
 constexpr int LENS_SEG_GRID_CTAS = 3;     // CTAs per SM one launch asks for: leaves room for the next step's walk CTAs
 #ifndef LENS_SEG_MIN_CTAS
 #define LENS_SEG_MIN_CTAS 5               // register budget: 96 per thread, nothing spilled inside the step loop
@@ -307,12 +311,11 @@ lens_seg_kernel(const __grid_constant__ Params P, int64_t first_index, const __g
     if ((unsigned long long)blockIdx.x * (LENS_THREADS / 32) >= n_groups) return;
     for (int i = threadIdx.x; i < P.tab_total; i += blockDim.x) smem_tab[i] = P.tab[i];
     block_acc_init(acc);
-    const bool reference_math = (P.flags & CMT_FLAG_REFERENCE_MATH) != 0;
-    const double r6 = rcp_refined(6.0);
     const DevElement &E = P.el[P.first_lens];
     const int n_steps = E.n_steps;
     const double bore_T = E.p[0];
     const Table tb = table_of(E, smem_tab);
+    const bool reference_math = (P.flags & CMT_FLAG_REFERENCE_MATH) != 0 || !tb.fast;
     const double r_last = tb.t[tb.n - 1].x;
     unsigned rows_total = 0, steps_total = 0, oob_total = 0, ref_total = 0;
 
@@ -346,11 +349,11 @@ lens_seg_kernel(const __grid_constant__ Params P, int64_t first_index, const __g
 
         bool dead = false;
         if (have) {
-#pragma unroll 1
+#pragma unroll LENS_UNROLL
             while (step < end_step) {
                 int oob = 0;
                 if (CONTRACT) lens_step_contracted(tb, r_last, lc, m, P.g, oob);
-                else lens_step(tb, lc, r6, m, s_xy, P.g, oob, reference_math);
+                else lens_step(tb, lc, m, s_xy, P.g, oob, reference_math);
                 oob_total += oob & 0xffff;
                 ref_total += oob >> 16;
                 ++steps_total;
@@ -572,7 +575,6 @@ __device__ __forceinline__ double random_double(uint64_t &s, int exp_lo, int exp
 __global__ void __launch_bounds__(256) selftest_kernel(int64_t n, uint64_t seed, int mode, unsigned long long *out)
 {
     unsigned long long c[5] = {0, 0, 0, 0, 0};
-    const double r6 = rcp_refined(6.0);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(i + 1));
         double a, b, sq;
@@ -580,18 +582,26 @@ __global__ void __launch_bounds__(256) selftest_kernel(int64_t n, uint64_t seed,
             a = random_double(s, -40, 12, true);
             b = random_double(s, -20, -4, false);
             sq = random_double(s, -40, -8, false);
-        } else if (mode == 1) {     // division by six
-            a = random_double(s, -60, 20, true);
-            b = 6.0;
-            sq = random_double(s, -200, 200, false);
+        } else if (mode == 1) {     // division by six: two-operation form against __ddiv_rn over the range StepCheck admits
+            a = random_double(s, (i & 1) ? -396 : -60, (i & 1) ? 1023 : 20, true);
+            const double q = div_by_six(a);
+            StepCheck chk;
+            chk.quotients(q, q);
+            if (chk.valid()) {
+                ++c[0];
+                if (__double_as_longlong(q) != __double_as_longlong(__ddiv_rn(a, 6.0))) ++c[1];
+            }
+            continue;
         } else if (mode == 3) {     // a / sqrt(sq) through the square root's own reciprocal estimate
-            a = random_double(s, -60, 20, true);
-            sq = random_double(s, -60, 20, false);
-            bool ok3 = true;
+            a = random_double(s, (i & 1) ? -800 : -60, (i & 1) ? 400 : 20, true);
+            sq = random_double(s, (i & 1) ? -960 : -60, (i & 1) ? 800 : 20, false);
+            StepCheck chk;
             double yr, early;
-            const double r = sqrt_rcp_fast(sq, ok3, yr, early);
-            const double q = div_rcp_mid(a, r, yr, ok3);
-            if (ok3) {
+            const double r = sqrt_rcp_fast(sq, chk.ok, yr, early);
+            const double q = div_by_root(a, r, yr);
+            chk.quotients(q, q);
+            // the step's own preconditions: r at most 2^400 (table_fast_ok), quotient at most 2^401
+            if (chk.valid() && r <= 0x1p400 && fabs(q) <= 0x1p401) {
                 ++c[0];
                 if (__double_as_longlong(q) != __double_as_longlong(__ddiv_rn(a, __dsqrt_rn(sq)))) ++c[1];
                 ++c[2];
@@ -605,7 +615,7 @@ __global__ void __launch_bounds__(256) selftest_kernel(int64_t n, uint64_t seed,
         }
         const double want = __ddiv_rn(a, b);
         bool ok = true;
-        const double y = (mode == 1) ? r6 : rcp_refined(b);
+        const double y = rcp_refined(b);
         const double q = div_rcp(a, b, y, ok);
         if (ok) { ++c[0]; if (__double_as_longlong(q) != __double_as_longlong(want)) ++c[1]; }
         if (__double_as_longlong(dvd_cached(a, b, y)) != __double_as_longlong(want)) ++c[4];

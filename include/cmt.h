@@ -242,8 +242,9 @@ int cmt_fp64_peak(int device, double *dfma_per_s, double *dadd_per_s);
 /* Arithmetic self-test on `device`: n pseudo-random operands compare the
  * shared-reciprocal division and the inline square root used by the kernels
  * with __ddiv_rn / __dsqrt_rn bit for bit.  mode 0: lens-integrator magnitudes,
- * 1: division by 6, 2: the whole binary64 range, 3: a / sqrt(s) with the reciprocal
- * taken from the square root's own iteration (the lens force's two divisions).  out[0] quotients that took the
+ * 1: w / 6 in its two-operation form (exponents -396 .. 1023), 2: the whole binary64 range,
+ * 3: a / sqrt(s) with the reciprocal taken from the square root's own iteration (the lens
+ * force's two divisions) under the RK step's validity record.  out[0] quotients that took the
  * short sequence, out[1] mismatches among them, out[2]/out[3] the same for
  * square roots, out[4] mismatches of the division with fallback. */
 int cmt_selftest(int device, int64_t n, uint64_t seed, int mode, int64_t out[5]);

@@ -296,12 +296,116 @@ def honeycomb_fixture(meta):
           "| aimed at cell 0:", dict(zip(names, np.bincount(res["fate"][n:n + k], minlength=len(names)))), flush=True)
 
 
+
+def table_builder_fixture(meta):
+    """The reference's OWN a_r(r) table builder (electrostatic_lens.py:174-213) executed as is:
+    `lens.lens_acceleration(x)` with a falsy `a_interp`, in a scratch cwd that holds an empty
+    `interpolation_functions/` directory (the builder pickles into it, :212-213).  The only substitution is
+    `stark_potential` in the reference module's namespace (centrex_TlF is absent): the build's
+    rigid-rotor curve, evaluated for the state the reference passes.  Pins linspace extent, nominal-dr gradient,
+    unit conversion and the interp1d hand-over, and the pickle cache on a second call."""
+    import os
+    import pickle
+    import tempfile
+
+    import trajectories.beamline_elements.electrostatic_lens as ref_lens
+    from centrex_TlF.states import UncoupledBasisState
+
+    calls = []
+
+    def stark(state, Ezs):
+        c = state.find_largest_component()
+        calls.append((int(c.J), int(c.mJ), len(Ezs)))
+        return _tlf.rigid_rotor_stark_joule(int(c.J), int(c.mJ), Ezs)
+
+    points = [  # (J, mJ, V, d)
+        (2, 0, 27.6e3, 1.75 * 0.0254),   # the default lens
+        (1, 1, 20e3, 1.75 * 0.0254),
+        (3, 0, 30e3, 1.75 * 0.0254),
+        (0, 0, 24e3, 1.75 * 0.0254),
+        (2, 1, 34e3, 1.5 * 0.0254),      # another bore: other grid length and extent
+        (3, 2, 27.6e3, 2.0 * 0.0254),
+    ]
+    out = dict(meta=json.dumps(meta), points=np.array(points, dtype=np.float64))
+    saved = ref_lens.stark_potential
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        os.mkdir(os.path.join(td, "interpolation_functions"))
+        os.chdir(td)
+        ref_lens.stark_potential = stark
+        try:
+            for k, (J, mJ, V, d) in enumerate(points):
+                state = 1 * UncoupledBasisState(J=J, mJ=mJ, I1=1 / 2, m1=1 / 2, I2=1 / 2, m2=-1 / 2, Omega=0, P=(-1) ** J,
+                                                electronic_state="X")
+                lens = ElectrostaticLens(z0=1.0, L=0.6, name="ES lens", d=d, V=V, state=state)
+                x = np.array([0.3 * d / 2, -0.2 * d / 2, 1.1])
+                a = lens.lens_acceleration(x)
+                out[f"r_{k}"], out[f"a_{k}"] = np.asarray(lens.a_interp.x), np.asarray(lens.a_interp.y)
+                out[f"x_{k}"], out[f"acc_{k}"] = x, np.asarray(a)
+                # second lens of the same configuration: must come from the pickle cache (:180-186), not the builder
+                n_calls = len(calls)
+                twin = ElectrostaticLens(z0=1.0, L=0.6, name="ES lens", d=d, V=V, state=state)
+                a2 = twin.lens_acceleration(x)
+                assert len(calls) == n_calls and np.array_equal(a, a2) and np.array_equal(twin.a_interp.y, lens.a_interp.y)
+            out["cache_files"] = np.array(sorted(os.listdir("interpolation_functions")))
+        finally:
+            ref_lens.stark_potential = saved
+            os.chdir(cwd)
+    np.savez_compressed(HERE / "table_builder.npz", **out)
+    print("table builder:", [(c, out[f"r_{k}"].shape[0]) for k, c in enumerate(calls)], flush=True)
+
+
+def run_simulation_fixtures(table, meta):
+    """run_simulation(n_jobs=1) of the reference on replayed draws (Counter keys in order of first occurrence,
+    saved list, row counts): the lens beamline saving Detected + Inside lens, the lens beamline saving an EARLY
+    fate (molecules stopped by the second aperture and at the lens entrance), and the SPA geometry with its
+    Gaussian position source."""
+    cases = {}
+    vbiased, xstd = CeNTREXVelocityDistribution(sigmax=3, sigmay=3), CeNTREXPositionDistribution()
+    ic = draw_reference(7, 1300, vbiased, xstd)
+    cases[""] = (lens_beamline(table), ic, 1234, ["Detected", "Inside lens"])
+    ic = draw_reference(8, 900, CeNTREXVelocityDistribution(sigmax=12, sigmay=12), xstd)
+    cases["early_"] = (lens_beamline(table), ic, 850, ["40K shield", "Lens entrance", "no such element"])
+    ic = np.concatenate([draw_reference(9, 700, CeNTREXVelocityDistribution(), GaussianPositionDistribution()),
+                         draw_reference(10, 500, CeNTREXVelocityDistribution(sigmax=1.5, sigmay=1.5),
+                                        GaussianPositionDistribution(sigmax=1e-3, sigmay=1e-3))], axis=1)
+    cases["spa_"] = (spa_beamline(), ic, 1200, ["Detected", "RC exit"])
+    out = dict(table_r=table[0], table_a=table[1], meta=json.dumps(meta), n_jobs=1)
+    for pre, (bl, ic, n_traj, aoi) in cases.items():
+        sim = TrajectorySimulator()
+        sim.run_simulation(bl, "golden", vdist=Replay(ic[3:6]), xdist=Replay(ic[0:3]), N_traj=n_traj,
+                           apertures_of_interest=aoi, n_jobs=1)
+        saved = sim.result.molecules
+        out.update({
+            pre + "ic": ic, pre + "N_traj": n_traj, pre + "aoi": np.array(aoi),
+            pre + "counter_keys": np.array(list(sim.counter.counter_dict.keys())),
+            pre + "counter_vals": np.array(list(sim.counter.counter_dict.values()), dtype=np.int64),
+            pre + "saved_x0": np.array([m.trajectory.x[0] for m in saved]).T.reshape(3, -1),
+            pre + "saved_fate": np.array([m.aperture_hit for m in saved]),
+            pre + "saved_n_rows": np.array([m.trajectory.x.shape[0] for m in saved], dtype=np.int32),
+            pre + "saved_last": np.array([np.concatenate([m.trajectory.x[-1], m.trajectory.v[-1], m.trajectory.a[-1],
+                                                          [m.trajectory.t[-1]]]) for m in saved]).reshape(-1, 10),
+            pre + "saved_alive": np.array([m.alive for m in saved]),
+            pre + "efficiency": sim.counter.calculate_efficiency()})
+        print(f"run_simulation[{pre or 'lens'}]: counter {sim.counter.counter_dict}, saved {len(saved)}", flush=True)
+    np.savez_compressed(HERE / "run_simulation.npz", **out)
+
+
 def main():
     t0 = time.time()
     meta = dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0],
                 reference="/root/reference (otimgren/centrex-molecule-trajectories)")
     table = lens_table()
     vstd, xstd = CeNTREXVelocityDistribution(), CeNTREXPositionDistribution()
+
+    # --- the reference's own table builder (python make_golden.py tables / runs regenerate single fixtures) ---
+    if sys.argv[1:] in ([], ["tables"]):
+        table_builder_fixture(meta)
+    if sys.argv[1:] == ["tables"]:
+        return
+    if sys.argv[1:] == ["runs"]:
+        run_simulation_fixtures(table, meta)
+        return
 
     # --- post-processing at planes (python make_golden.py planes regenerates only this fixture) ---
     if sys.argv[1:] != ["honeycomb"]:
@@ -367,25 +471,8 @@ def main():
           f"  [{time.time() - t0:.0f}s]", flush=True)
 
     # --- run_simulation itself (n_jobs=1) on replayed draws: Counter + saved list semantics ---
-    ic = draw_reference(7, 1300, CeNTREXVelocityDistribution(sigmax=3, sigmay=3), xstd)
-    sim = TrajectorySimulator()
-    bl = lens_beamline(table)
-    aoi = ["Detected", "Inside lens"]
-    sim.run_simulation(bl, "golden", vdist=Replay(ic[3:6]), xdist=Replay(ic[0:3]), N_traj=1234,
-                       apertures_of_interest=aoi, n_jobs=1)
-    saved = sim.result.molecules
-    saved_x0 = np.array([m.trajectory.x[0] for m in saved]).T
-    np.savez_compressed(
-        HERE / "run_simulation.npz", ic=ic, table_r=table[0], table_a=table[1],
-        meta=json.dumps(meta), N_traj=1234, n_jobs=1, aoi=np.array(aoi),
-        counter_keys=np.array(list(sim.counter.counter_dict.keys())),
-        counter_vals=np.array(list(sim.counter.counter_dict.values()), dtype=np.int64),
-        saved_x0=saved_x0, saved_fate=np.array([m.aperture_hit for m in saved]),
-        saved_n_rows=np.array([m.trajectory.x.shape[0] for m in saved], dtype=np.int32),
-        saved_alive=np.array([m.alive for m in saved]),
-        efficiency=sim.counter.calculate_efficiency())
-    print(f"run_simulation: counter {sim.counter.counter_dict}, saved {len(saved)}"
-          f"  [{time.time() - t0:.0f}s]", flush=True)
+    run_simulation_fixtures(table, meta)
+    print(f"  [{time.time() - t0:.0f}s]", flush=True)
 
 
 if __name__ == "__main__":

@@ -240,8 +240,11 @@ def test_host_buffer_entry(torch_cuda, cuda_lib):
     assert relerr(fin, want["fin"]) < TIGHT
 
 
-def test_run_simulation_golden(torch_cuda, golden_dir):
-    """TrajectorySimulator.run_simulation on replayed draws == the reference's own run."""
+@pytest.mark.parametrize("case", ["", "early_", "spa_"])
+def test_run_simulation_golden(torch_cuda, golden_dir, case):
+    """TrajectorySimulator.run_simulation on replayed draws == the reference's own run (trajectory_simulator.py:34-103):
+    the lens beamline saving Detected + Inside lens, the lens beamline saving EARLY fates (second aperture, lens
+    entrance, and a name that matches nothing), and the SPA geometry with its Gaussian source."""
     from trajectories.distributions import Distribution
     from trajectories.trajectory_simulator import TrajectorySimulator
 
@@ -259,10 +262,12 @@ def test_run_simulation_golden(torch_cuda, golden_dir):
         def save_to_hdf(self, *a, **k):
             pass
 
-    bl = lens_beamline((g["table_r"], g["table_a"]))
+    full = g
+    g = {k[len(case):]: full[k] for k in full.files if k.startswith(case)} if case else full
+    bl = spa_beamline() if case == "spa_" else lens_beamline((full["table_r"], full["table_a"]))
     sim = TrajectorySimulator()
     sim.run_simulation(bl, "golden", vdist=Replay(g["ic"][3:6]), xdist=Replay(g["ic"][0:3]),
-                       N_traj=int(g["N_traj"]), apertures_of_interest=list(g["aoi"]), n_jobs=int(g["n_jobs"]))
+                       N_traj=int(g["N_traj"]), apertures_of_interest=list(g["aoi"]), n_jobs=int(full["n_jobs"]))
     want = dict(zip(g["counter_keys"].tolist(), g["counter_vals"].tolist()))
     assert sim.counter.counter_dict == want
     assert sim.counter.calculate_efficiency() == float(g["efficiency"])
@@ -272,6 +277,9 @@ def test_run_simulation_golden(torch_cuda, golden_dir):
     assert [m.alive for m in saved] == g["saved_alive"].tolist()
     assert [m.trajectory.x.shape[0] for m in saved] == g["saved_n_rows"].tolist()
     np.testing.assert_array_equal(np.array([m.trajectory.x[0] for m in saved]).T, g["saved_x0"])
+    last = np.array([np.concatenate([m.trajectory.x[-1], m.trajectory.v[-1], m.trajectory.a[-1], [m.trajectory.t[-1]]])
+                     for m in saved])
+    assert relerr(last, g["saved_last"]) < TIGHT
     assert sim.results["golden"].counter is sim.counter
     m = saved[0]
     assert m.trajectory.x.shape[1] == 3 and m.trajectory.v.shape == m.trajectory.a.shape == m.trajectory.x.shape
@@ -329,15 +337,19 @@ def test_arithmetic_selftest(torch_cuda, cuda_lib):
     """The shared-reciprocal division and inline sqrt equal __ddiv_rn / __dsqrt_rn bit for bit."""
     import ctypes as C
 
-    for mode, n in ((0, 100_000_000_000), (1, 100_000_000_000), (2, 100_000_000_000)):
+    for mode, n in ((0, 100_000_000_000), (1, 100_000_000_000), (2, 100_000_000_000), (3, 100_000_000_000)):
         out = (C.c_int64 * 5)()
         assert cuda_lib.cmt_selftest(0, n, 0xC0FFEE + mode, mode, out) == 0, cuda_lib.cmt_last_error()
         took_div, bad_div, took_sqrt, bad_sqrt, bad_cached = list(out)
         assert bad_div == 0 and bad_sqrt == 0 and bad_cached == 0, (mode, list(out))
-        if mode < 2:
+        if mode == 0:
             assert took_div == n and took_sqrt == n        # the short sequences cover the working range
-        else:
+        elif mode == 1:
+            assert took_div == n                           # w/6 in two operations: every operand StepCheck admits
+        elif mode == 2:
             assert 0.5 * n < took_div < n and took_sqrt > 0.9 * n   # extremes fall back
+        else:
+            assert took_div > 0.3 * n and took_sqrt == took_div     # a / sqrt(s) with the root's own reciprocal
 
 
 def test_fast_math_equals_reference_math(torch_cuda, cuda_lib):
