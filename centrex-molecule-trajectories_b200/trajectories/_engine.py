@@ -16,7 +16,7 @@ import numpy as np
 from . import _native as nat
 
 G = 9.80665  # scipy.constants.g (molecule.py:6)
-DEFAULT_CHUNK = 1 << 26          # molecules per launch: 4.3 GB of lens-queue workspace per stream slot; larger
+DEFAULT_CHUNK = 1 << 26          # molecules per launch: 8.6 GB of lens-queue workspace per stream slot (2 x 64 B per molecule); larger
                                  # launches keep the lens integrator's lanes refilled (1e10 molecules: 0.81 s at
                                  # 2^24, 0.73 s at 2^26)
 ROW_BUDGET_BYTES = 1 << 30       # device bytes per saved-trajectory batch
@@ -572,9 +572,56 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def owned_draws(vdist, xdist, N: int, N_loops: int, rank: int, world: int):
+    """The (velocities, positions) chunks of the reference's draw loop (trajectory_simulator.py:57-58) that belong
+    to `rank`: a contiguous block of the N_loops chunks.  Every rank draws from chunk 0 on and discards the
+    chunks of lower ranks, so ranks whose generators are seeded identically end up with disjoint pieces of one
+    sample (see run_simulation)."""
+    if N == 0:
+        return
+    lo_loop, hi_loop = shard_range(N_loops, rank, world)
+    for loop in range(hi_loop):
+        vs = np.asarray(vdist.draw(N), dtype=np.float64)   # velocities first, as the reference
+        xs = np.asarray(xdist.draw(N), dtype=np.float64)
+        if vs.shape != (3, N) or xs.shape != (3, N):
+            raise ValueError(f"Distribution.draw({N}) must return shape (3, {N})")
+        if loop >= lo_loop:
+            yield vs, xs
+
+
 def allreduce_counts(t):
     """Sum an int64 tensor over ranks (the Counter merge, trajectory_simulator.py:147-158)."""
     torch = _torch()
     if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
     return t
+
+
+def gather_counts(n: int, device=None) -> List[int]:
+    """all_gather of one int64 per rank (the saved-trajectory counts): every rank learns how many
+    molecules each rank saved, hence the global number of its own first saved molecule."""
+    torch = _torch()
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()) or torch.distributed.get_world_size() == 1:
+        return [int(n)]
+    dist = torch.distributed
+    dev = torch.device("cuda", device) if (dist.get_backend() == "nccl" and device is not None) else torch.device("cpu")
+    mine = torch.tensor([int(n)], dtype=torch.int64, device=dev)
+    out = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, mine)
+    return [int(t.item()) for t in out]
+
+
+def broadcast_object(obj, src: int = 0):
+    """Small Python object from rank `src` to every rank (a no-op without torch.distributed)."""
+    torch = _torch()
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()) or torch.distributed.get_world_size() == 1:
+        return obj
+    box = [obj]
+    torch.distributed.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def barrier():
+    torch = _torch()
+    if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        torch.distributed.barrier()

@@ -1,7 +1,8 @@
-"""HDF5 result layout of the reference, written through h5py.
+"""HDF5 result layout of the reference.
 
-h5py is an optional dependency (absent from the build image): importing this
-module never needs it, calling a save function does.
+Written through h5py when it is installed, otherwise through the package's own
+dependency-free HDF5 writer/reader (`_minih5`, same interface, same file format),
+so results can be saved and re-imported on a machine without libhdf5.
 
   /<run>/counter                        attrs {fate: count}            (trajectory_simulator.py:160-177)
   /<run>/beamline/<element.name>        attrs class + vars(element)    (apertures.py:56-80)
@@ -13,11 +14,17 @@ from __future__ import annotations
 
 
 def h5py():
+    """The HDF5 module to use: h5py if importable, else the built-in `_minih5`."""
     try:
         import h5py as _h5
-    except ImportError as e:
-        raise ImportError("saving results to HDF5 needs h5py, which is not installed") from e
-    return _h5
+
+        if _h5 is not None:
+            return _h5
+    except ImportError:
+        pass
+    from . import _minih5
+
+    return _minih5
 
 
 def save_element(element, filepath, parent_group_path: str) -> None:

@@ -21,7 +21,7 @@ from __future__ import annotations
 
 import os
 from copy import copy
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from pathlib import Path
 from typing import List, Optional
 
@@ -68,11 +68,20 @@ class Counter:
 
 @dataclass
 class SimulationResult:
+    """counter, beamline, xdist, vdist, molecules: the reference's five fields (trajectory_simulator.py:180-191).
+
+    Under torch.distributed every rank holds the molecules of its own block of the global index range, in global
+    order; `molecule_offset` is the number of molecules saved by lower ranks (from an all_gather of the per-rank
+    counts) and `n_molecules_total` the sum over ranks, so that `save_to_hdf` numbers `molecule_<i>` globally and
+    the file written by N ranks equals the file of a single-GPU run.
+    """
     counter: Counter
     beamline: Beamline
     xdist: Distribution
     vdist: Distribution
     molecules: List[Molecule]
+    molecule_offset: int = field(default=0, compare=False)
+    n_molecules_total: Optional[int] = field(default=None, compare=False)
 
     def plot(self, N_max: int = 10000, elements: List[str] = None, show: bool = True):
         axes = self.beamline.plot()
@@ -90,30 +99,69 @@ class SimulationResult:
             plt.show()
         return axes
 
-    def save_to_hdf(self, filepath: Path, run_name: str) -> None:
+    def save_to_hdf(self, filepath: Path, run_name: str, packed: bool = False) -> None:
+        """The reference's layout (trajectory_simulator.py:218-254).  `packed=True` stores the trajectories as one
+        `(total_rows, 10)` dataset with row offsets instead of a group and four datasets per molecule.
+
+        Under torch.distributed rank 0 writes the run's metadata, then the ranks append their molecules one after
+        the other in rank order (the file must be on a filesystem all ranks see)."""
         from ._hdf import h5py
 
-        with h5py().File(filepath, "a") as f:
-            try:
-                f.create_group(run_name)
-            except ValueError:
-                if input("Run name already exists. Overwrite? y/n") != "y":
-                    return
-                del f[run_name]
-                f.create_group(run_name)
-        attributes = copy(vars(self))
-        attributes.pop("molecules")
-        for value in attributes.values():
-            value.save_to_hdf(filepath, run_name)
-        self.save_molecules_to_hdf(filepath, run_name)
+        rank, world = eng.dist_info()
+        proceed = True
+        if rank == 0:
+            with h5py().File(filepath, "a") as f:
+                try:
+                    f.create_group(run_name)
+                except ValueError:
+                    if input("Run name already exists. Overwrite? y/n") != "y":
+                        proceed = False
+                    else:
+                        del f[run_name]
+                        f.create_group(run_name)
+            if proceed:
+                for key in ("counter", "beamline", "xdist", "vdist"):
+                    getattr(self, key).save_to_hdf(filepath, run_name)
+        proceed = eng.broadcast_object(proceed)
+        if not proceed:
+            return
+        for turn in range(world):
+            if turn == rank:
+                self.save_molecules_to_hdf(filepath, run_name, packed=packed)
+            eng.barrier()
 
-    def save_molecules_to_hdf(self, filepath: Path, run_name: str) -> None:
+    def save_molecules_to_hdf(self, filepath: Path, run_name: str, packed: bool = False) -> None:
         from ._hdf import h5py
 
         print("Saving trajectories...")
         with h5py().File(filepath, "a") as f:
-            for i, molecule in enumerate(self.molecules):
+            if packed:
+                self._save_packed(f, run_name)
+                return
+            for i, molecule in enumerate(self.molecules, self.molecule_offset):
                 molecule.save_to_hdf(f, run_name, f"trajectories/molecule_{i}")
+
+    def _save_packed(self, f, run_name: str) -> None:
+        """<run>/trajectories_packed[/rank_<r>]: rows (total_rows, 10) = x,y,z,vx,vy,vz,ax,ay,az,t; offsets (n+1,);
+        fate (n,) indices into the attribute `fate_names`; alive (n,); attribute first_molecule = global number of
+        molecule 0 of the block."""
+        rank, world = eng.dist_info()
+        path = run_name + "/trajectories_packed" + (f"/rank_{rank}" if world > 1 else "")
+        g = f.create_group(path)
+        names = sorted({m.aperture_hit for m in self.molecules})
+        counts = np.array([m.trajectory.n for m in self.molecules], dtype=np.int64)
+        offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        rows = np.empty((int(offsets[-1]), 10))
+        for k, m in enumerate(self.molecules):
+            tr = m.trajectory
+            lo, hi = offsets[k], offsets[k + 1]
+            rows[lo:hi, 0:3], rows[lo:hi, 3:6], rows[lo:hi, 6:9], rows[lo:hi, 9] = tr.x, tr.v, tr.a, tr.t
+        g.create_dataset("rows", data=rows)
+        g.create_dataset("offsets", data=offsets)
+        g.create_dataset("fate", data=np.array([names.index(m.aperture_hit) for m in self.molecules], dtype=np.int32))
+        g.create_dataset("alive", data=np.array([bool(m.alive) for m in self.molecules], dtype=np.uint8))
+        g.attrs["fate_names"] = np.array(names, dtype=object) if names else np.array([], dtype="S1")
+        g.attrs["first_molecule"] = int(self.molecule_offset)
 
 
 class TrajectorySimulator:
@@ -121,9 +169,12 @@ class TrajectorySimulator:
 
     def __init__(self, device=None, seed: Optional[int] = None, chunk: int = eng.DEFAULT_CHUNK,
                  math: str = "exact") -> None:
-        """math="exact" (default) reproduces the reference bit for bit; math="contracted" runs the same
-        algorithm with fused multiply-adds and reciprocal multiplications (agreement to ~1e-13 relative (1e-9 in the worst case, on coordinates that pass near zero),
-        1.3-1.6x the lens-integrator throughput)."""
+        """math="exact" (default): every operation rounds as in the reference, in the reference's order -- fates are
+        the reference's fates and rows agree to the last bit except where DESIGN.md "Exact arithmetic" lists a known
+        difference (NumPy's scalar `dt**2` goes through libm pow(): <= 1 ulp in y in ~1e-5 of ballistic steps; a
+        literal -0.0 input becomes +0.0).  math="contracted" runs the same algorithm with fused multiply-adds and
+        reciprocal multiplications (agreement to ~1e-13 relative, 1e-9 in the worst case on coordinates that pass
+        near zero; 1.2x the lens-integrator throughput)."""
         self.counter = Counter()
         self.results = {}
         self.device = device
@@ -186,9 +237,14 @@ class TrajectorySimulator:
                     molecules.extend(self._collect(prop, ic))
             prop.join()
         else:
-            # host draws, replayed: loop l of the reference's N_loops belongs to rank l % world
+            # Host draws, replayed.  The reference's N_loops chunks are split into one contiguous block of loops per
+            # rank.  A Distribution object is opaque (it may draw from NumPy's global RNG, which scripts seed the same
+            # way in every process), so every rank walks through the draws in the reference's order and throws away
+            # the chunks of lower ranks: identically seeded ranks then simulate DISJOINT pieces of one and the same
+            # sample -- the union, in rank order, is the single-process run -- instead of world copies of the same
+            # molecules; differently seeded ranks simulate independent samples.  Costs rank r its share of the
+            # draws times r + 1; the built-in distributions never come here (Philox on the device).
             batch_v, batch_x, filled = [], [], 0
-            loops = range(rank, N_loops, world)
 
             def flush():
                 nonlocal batch_v, batch_x, filled
@@ -201,13 +257,7 @@ class TrajectorySimulator:
                     molecules.extend(self._collect(prop, ic, select=res.saved_index))
                 batch_v, batch_x, filled = [], [], 0
 
-            for _ in loops:
-                if N == 0:
-                    break
-                vs = np.asarray(vdist.draw(N), dtype=np.float64)   # velocities first, :57-58
-                xs = np.asarray(xdist.draw(N), dtype=np.float64)
-                if vs.shape != (3, N) or xs.shape != (3, N):
-                    raise ValueError(f"Distribution.draw({N}) must return shape (3, {N})")
+            for vs, xs in eng.owned_draws(vdist, xdist, N, N_loops, rank, world):
                 batch_v.append(vs)
                 batch_x.append(xs)
                 filled += N
@@ -228,8 +278,12 @@ class TrajectorySimulator:
         for name, c in zip(flat.fate_names, counts):
             if c > 0:
                 self.counter.increment_counter(name, int(c))
-        self.result = SimulationResult(self.counter, beamline, xdist, vdist, molecules)
-        self.results[run_name] = SimulationResult(self.counter, beamline, xdist, vdist, molecules)
+        # the gather of the saved-trajectory counts: every rank keeps its own molecules (rank order = global order) and
+        # learns the global number of its first one, so that save_to_hdf numbers molecule_<i> as a single-GPU run does
+        saved_counts = eng.gather_counts(len(molecules), prop.device)
+        offset, n_saved = sum(saved_counts[:rank]), sum(saved_counts)
+        self.result = SimulationResult(self.counter, beamline, xdist, vdist, molecules, offset, n_saved)
+        self.results[run_name] = SimulationResult(self.counter, beamline, xdist, vdist, molecules, offset, n_saved)
 
     # the reference's README calls the parallel entry point by this name (README.md:52)
     run_simulation_parallel = run_simulation
@@ -301,11 +355,7 @@ class TrajectorySimulator:
                 else:
                     prop.propagate_philox(source, seed, first, n)
         else:
-            for _ in range(rank, N_loops, world):
-                if N == 0:
-                    break
-                vs = np.asarray(vdist.draw(N), dtype=np.float64)   # velocities first, :57-58
-                xs = np.asarray(xdist.draw(N), dtype=np.float64)
+            for vs, xs in eng.owned_draws(vdist, xdist, N, N_loops, rank, world):
                 ic = torch.from_numpy(np.ascontiguousarray(np.concatenate([xs, vs]), dtype=np.float64)).to(prop.tdev)
                 if mask is None:
                     probe(ic)
@@ -334,5 +384,12 @@ class TrajectorySimulator:
         from_rows = Molecule.from_rows
         lo = np.asarray(offsets).tolist()
         # each trajectory is a view of its slice of the result block
-        return [from_rows(rows[lo[k]:lo[k + 1]], names[f], names[f] == "Detected")
+        mols = [from_rows(rows[lo[k]:lo[k + 1]], names[f], names[f] == "Detected")
                 for k, f in enumerate(np.asarray(fate).tolist())]
+        if rows.size and not np.isfinite(rows).all():
+            # Beamline.propagate_through ends with trajectory.drop_nans() (beamline.py:38, molecule.py:160-167), which
+            # also strips rows that a non-finite initial condition or an overflow filled with NaN / inf
+            for m in mols:
+                m.trajectory.drop_nans()
+                m.trajectory.n = m.trajectory.t.shape[0]
+        return mols

@@ -11,6 +11,8 @@ import inspect
 from pathlib import Path
 from typing import List
 
+import numpy as np
+
 from ._hdf import h5py
 from .beamline import Beamline
 from .molecule import Molecule, Trajectory
@@ -52,9 +54,27 @@ def import_beamline_from_hdf(filepath: Path, run_name: str) -> Beamline:
     return Beamline([import_element_from_hdf(n, filepath, run_name) for n in names])
 
 
+def _packed_blocks(grp):
+    """The blocks of a packed trajectory group, in global molecule order (one per rank of the run that wrote it)."""
+    if "rows" in grp:
+        return [grp]
+    blocks = [grp[k] for k in grp.keys()]
+    return sorted(blocks, key=lambda b: int(_plain(b.attrs["first_molecule"])))
+
+
 def import_trajectories_from_hdf(filepath: Path, run_name: str, group_name: str = "trajectories") -> List[Molecule]:
+    """Molecules of a run: the reference's group-per-molecule layout (utils.py:63-105; molecules come back in the
+    group's name order, i.e. molecule_0, molecule_1, molecule_10, ... exactly as with h5py), or, when that group is
+    absent, the packed layout written by `save_to_hdf(..., packed=True)` (global molecule order)."""
     molecules = []
     with h5py().File(filepath, "r") as f:
+        if group_name == "trajectories" and (run_name + "/trajectories") not in f and (run_name + "/trajectories_packed") in f:
+            for block in _packed_blocks(f[run_name + "/trajectories_packed"]):
+                rows, offsets = block["rows"][()], block["offsets"][()]
+                names = [_plain(n) for n in np.atleast_1d(block.attrs["fate_names"])]
+                for k, (fate, alive) in enumerate(zip(block["fate"][()], block["alive"][()])):
+                    molecules.append(Molecule.from_rows(rows[offsets[k]:offsets[k + 1]], names[fate], bool(alive)))
+            return molecules
         grp = f[run_name + "/" + group_name]
         for name in list(grp.keys()):
             g = grp[name]

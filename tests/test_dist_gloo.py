@@ -58,3 +58,116 @@ def test_shard_and_allreduce_world2(tmp_path):
     whole = oracle.run(bl.elements, src, seed=4, first=0, n=total)["counters"]
     np.testing.assert_array_equal(r0[1], whole)                 # GPU-count invariance of the result
     assert whole.sum() == total
+
+
+# ---------------------------------------------------------------------------
+# saved trajectories across ranks: the gather of the saved counts, global molecule numbering, one merged file
+# ---------------------------------------------------------------------------
+def _fake_molecules(lo, hi):
+    """Molecule k of a pretend run: k % 4 + 2 rows whose values encode k."""
+    from trajectories.molecule import Molecule
+
+    out = []
+    for k in range(lo, hi):
+        rows = (np.arange((k % 4 + 2) * 10, dtype=float).reshape(-1, 10) + 1000.0 * k)
+        out.append(Molecule.from_rows(rows, "Detected" if k % 3 else "Inside lens", bool(k % 3)))
+    return out
+
+
+def _result(mols, offset=0, total=None):
+    from tests.beamlines import apertures_beamline
+    from trajectories.distributions import CeNTREXPositionDistribution, CeNTREXVelocityDistribution
+    from trajectories.trajectory_simulator import Counter, SimulationResult
+
+    c = Counter()
+    c.increment_counter("Detected", 7)
+    return SimulationResult(c, apertures_beamline(), CeNTREXPositionDistribution(), CeNTREXVelocityDistribution(), mols,
+                            offset, total)
+
+
+def _save_worker(rank, world, port, out_dir, packed):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    for p in (str(ROOT), str(ROOT / "centrex-molecule-trajectories_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    sys.modules["h5py"] = None                      # the built-in writer, as on the GPU box
+    import torch.distributed as dist
+
+    from trajectories import _engine as eng
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cuts = [0, 5, 5, 14][: world + 1] if world == 3 else [0, 5, 14]       # rank 1 of 3 saved nothing
+    mols = _fake_molecules(cuts[rank], cuts[rank + 1])
+    counts = eng.gather_counts(len(mols))
+    assert counts == [cuts[r + 1] - cuts[r] for r in range(world)]
+    res = _result(mols, sum(counts[:rank]), sum(counts))
+    res.save_to_hdf(Path(out_dir) / "merged.hdf", "run/a", packed=packed)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,packed", [(2, False), (3, False), (2, True)])
+def test_ranks_write_one_file_numbered_like_a_single_run(tmp_path, monkeypatch, world, packed):
+    """SimulationResult.save_to_hdf under torch.distributed: metadata once, molecules of rank r numbered from the
+    count saved by ranks < r (reference numbering trajectory_simulator.py:251-254 over the flat list of :86-91)."""
+    import torch.multiprocessing as mp
+
+    from trajectories import _minih5, utils
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_save_worker, args=(world, port, str(tmp_path), packed), nprocs=world, join=True)
+    monkeypatch.setitem(sys.modules, "h5py", None)
+    single = tmp_path / "single.hdf"
+    _result(_fake_molecules(0, 14)).save_to_hdf(single, "run/a", packed=packed)
+    with _minih5.File(tmp_path / "merged.hdf", "r") as m, _minih5.File(single, "r") as s1:
+        assert m["run/a"].keys() == s1["run/a"].keys()
+        assert dict(m["run/a/counter"].attrs.items()) == dict(s1["run/a/counter"].attrs.items())
+        assert m["run/a/beamline"].keys() == s1["run/a/beamline"].keys()
+        if not packed:
+            assert m["run/a/trajectories"].keys() == s1["run/a/trajectories"].keys()
+            assert len(m["run/a/trajectories"]) == 14
+            for name in s1["run/a/trajectories"].keys():
+                a, b = m["run/a/trajectories"][name], s1["run/a/trajectories"][name]
+                for key in ("x", "v", "a", "t"):
+                    np.testing.assert_array_equal(a[key][()], b[key][()])
+                assert dict(a.attrs.items()) == dict(b.attrs.items())
+    merged = utils.import_trajectories_from_hdf(tmp_path / "merged.hdf", "run/a")
+    alone = utils.import_trajectories_from_hdf(single, "run/a")
+    assert len(merged) == len(alone) == 14
+    for a, b in zip(merged, alone):
+        np.testing.assert_array_equal(a.trajectory.x, b.trajectory.x)
+        np.testing.assert_array_equal(a.trajectory.t, b.trajectory.t)
+        assert a.aperture_hit == b.aperture_hit and a.alive == b.alive
+    if packed:                                      # packed blocks come back in global molecule order
+        assert [m.trajectory.x[0, 0] for m in merged] == [1000.0 * k for k in range(14)]
+
+
+def test_identically_seeded_ranks_draw_disjoint_pieces():
+    """Host-drawn (custom) distributions under torch.distributed: ranks that seed NumPy's global generator the same
+    way must not simulate the same molecules.  Each rank owns a contiguous block of the reference's draw loops
+    (trajectory_simulator.py:52-58) and skips the draws of lower ranks, so the pieces, in rank order, are exactly
+    the single-process sample."""
+    from trajectories import _engine as eng
+    from trajectories.distributions import CeNTREXVelocityDistribution, GaussianPositionDistribution
+
+    class Shifted(GaussianPositionDistribution):     # a user-defined Distribution: no device generator for it
+        def draw(self, n):
+            return super().draw(n) + 1.0
+
+    assert eng.make_source(CeNTREXVelocityDistribution(), Shifted()) is None
+    N, loops = 7, 10
+    np.random.seed(5)
+    whole = list(eng.owned_draws(CeNTREXVelocityDistribution(), Shifted(), N, loops, 0, 1))
+    assert len(whole) == loops
+    pieces = []
+    for rank in range(3):
+        np.random.seed(5)                            # every rank runs the same script
+        pieces += list(eng.owned_draws(CeNTREXVelocityDistribution(), Shifted(), N, loops, rank, 3))
+    assert len(pieces) == loops
+    for (v0, x0), (v1, x1) in zip(whole, pieces):
+        np.testing.assert_array_equal(v0, v1)
+        np.testing.assert_array_equal(x0, x1)
+    firsts = {p[0][0, 0] for p in pieces}
+    assert len(firsts) == loops                      # no chunk twice
+    assert list(eng.owned_draws(CeNTREXVelocityDistribution(), Shifted(), 0, loops, 0, 1)) == []

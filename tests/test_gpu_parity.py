@@ -377,7 +377,9 @@ def test_fast_math_equals_reference_math(torch_cuda, cuda_lib):
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     np.testing.assert_array_equal(outs[0][1].view(np.int64), outs[1][1].view(np.int64))
     np.testing.assert_array_equal(outs[0][2][:4], outs[1][2][:4])
-    assert outs[0][2][4] == 0 and outs[1][2][4] == outs[1][2][1]     # RK steps on the plain-intrinsic path: none / all
+    # RK steps on the plain-intrinsic path: a few per 1e7 (a radius within 2^-20 of its table interval's end fails
+    # the one-comparison interval test and is redone there) / all
+    assert outs[0][2][4] <= 1e-5 * outs[0][2][1] and outs[1][2][4] == outs[1][2][1]
     np.testing.assert_array_equal(outs[0][4], outs[1][4])
     np.testing.assert_array_equal(outs[0][3].view(np.int64), outs[1][3].view(np.int64))
     assert outs[0][2][1] > 50_000_000                      # tens of millions of RK steps compared

@@ -73,10 +73,24 @@ def test_existing_run_prompts_before_overwrite(h5, tmp_path, monkeypatch):
     assert h5.File(path, "r")["r/counter"].attrs["Detected"] == 3
 
 
-def test_missing_h5py_is_reported(tmp_path, monkeypatch):
+def test_without_h5py_the_builtin_writer_is_used(tmp_path, monkeypatch):
+    """No h5py: the same calls write a real HDF5 file through trajectories._minih5 and read it back."""
+    from trajectories import _hdf, _minih5, utils
+
     monkeypatch.setitem(sys.modules, "h5py", None)
-    with pytest.raises(ImportError, match="h5py"):
-        make_result().save_to_hdf(tmp_path / "x.hdf", "r")
+    assert _hdf.h5py() is _minih5
+    res = make_result()
+    path = tmp_path / "x.hdf"
+    res.save_to_hdf(path, "lens run/2022")
+    assert path.read_bytes()[:8] == b"\x89HDF\r\n\x1a\n"
+    back = utils.import_sim_result_from_hdf(path, "lens run/2022")
+    assert back.counter.counter_dict == res.counter.counter_dict
+    assert [e.name for e in back.beamline.elements] == [e.name for e in res.beamline.elements]   # Beamline sorts by z0
+    assert back.xdist == res.xdist and back.vdist == res.vdist
+    for a, b in zip(back.molecules, res.molecules):
+        np.testing.assert_array_equal(a.trajectory.x, b.trajectory.x)
+        np.testing.assert_array_equal(a.trajectory.a, b.trajectory.a)
+        assert a.aperture_hit == b.aperture_hit and a.alive == b.alive
 
 
 def test_round_trip_through_utils(h5, tmp_path):

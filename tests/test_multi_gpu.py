@@ -33,7 +33,25 @@ def _worker(rank, world, port, out_dir):
     # plane probe: same sharding, Counter all-reduced, crossings stay on the owning rank
     xy, v = sim.plane_distributions(lens_beamline(lens_table()), 2.0, elements=["Detected"], N_traj=3_000_000, n_jobs=10)
     assert sim.counter.counter_dict == dict(zip(keys, vals))
-    np.savez(Path(out_dir) / f"rank{rank}.npz", keys=np.array(keys), vals=np.array(vals), saved=first_rows, xy=xy, v=v)
+    # the merged result file: rank 0 writes the metadata, the ranks append their molecules in turn, numbered globally
+    sys.modules["h5py"] = None
+    run = TrajectorySimulator(device=rank, seed=21, chunk=1 << 20)
+    run.run_simulation(lens_beamline(lens_table()), "r", N_traj=3_000_000, apertures_of_interest=["Detected"], n_jobs=10)
+    run.result.save_to_hdf(Path(out_dir) / "merged.hdf", "r")
+    # a user-defined Distribution is drawn on the host: identically seeded ranks must simulate disjoint molecules
+    from trajectories.distributions import CeNTREXVelocityDistribution
+
+    class Narrow(CeNTREXVelocityDistribution):
+        pass
+
+    np.random.seed(99)
+    custom = TrajectorySimulator(device=rank)
+    custom.run_simulation(lens_beamline(lens_table()), "c", vdist=Narrow(sigmax=3, sigmay=3), N_traj=40_000,
+                          apertures_of_interest=["Detected"], n_jobs=1)
+    np.savez(Path(out_dir) / f"rank{rank}.npz", keys=np.array(keys), vals=np.array(vals), saved=first_rows, xy=xy, v=v,
+             offset=run.result.molecule_offset, total=run.result.n_molecules_total,
+             ckeys=np.array(list(custom.counter.counter_dict.keys())), cvals=np.array(list(custom.counter.counter_dict.values())),
+             csaved=np.array([m.trajectory.x[0] for m in custom.result.molecules]).reshape(-1, 3))
     dist.destroy_process_group()
 
 
@@ -65,3 +83,29 @@ def test_two_ranks_equal_one(tmp_path):
     np.testing.assert_array_equal(np.concatenate([r0["xy"], r1["xy"]]), xy)
     np.testing.assert_array_equal(np.concatenate([r0["v"], r1["v"]]), v)
     assert xy.shape[0] == single.shape[0] > 100
+    # the gather of the saved counts: global numbers of each rank's first saved molecule, and one merged file
+    assert int(r0["offset"]) == 0 and int(r1["offset"]) == r0["saved"].reshape(-1, 3).shape[0]
+    assert int(r0["total"]) == int(r1["total"]) == single.shape[0]
+    from trajectories import utils
+
+    sys.modules["h5py"] = None
+    sim.result.save_to_hdf(tmp_path / "single.hdf", "r")
+    merged = utils.import_trajectories_from_hdf(tmp_path / "merged.hdf", "r")
+    alone = utils.import_trajectories_from_hdf(tmp_path / "single.hdf", "r")
+    assert len(merged) == len(alone) == single.shape[0]
+    for a, b in zip(merged, alone):                                # same molecule_<i> names, same contents
+        np.testing.assert_array_equal(a.trajectory.x, b.trajectory.x)
+        np.testing.assert_array_equal(a.trajectory.v, b.trajectory.v)
+    # host-drawn custom distribution, every rank seeded alike: together the ranks are the single-process run
+    from trajectories.distributions import CeNTREXVelocityDistribution
+
+    class Narrow(CeNTREXVelocityDistribution):
+        pass
+
+    np.random.seed(99)
+    one = TrajectorySimulator(device=0)
+    one.run_simulation(lens_beamline(lens_table()), "c", vdist=Narrow(sigmax=3, sigmay=3), N_traj=40_000,
+                       apertures_of_interest=["Detected"], n_jobs=1)
+    assert {k: int(v) for k, v in zip(r0["ckeys"], r0["cvals"])} == one.counter.counter_dict
+    np.testing.assert_array_equal(np.concatenate([r0["csaved"], r1["csaved"]]),
+                                  np.array([m.trajectory.x[0] for m in one.result.molecules]).reshape(-1, 3))
