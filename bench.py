@@ -48,10 +48,59 @@ WORKLOAD = ("configs[1]: examples/lens_simulation_beamline.py full CeNTREX beaml
 # 1e7 molecules (profiles/r01_full_f_segments.txt); scaled linearly when --molecules differs
 NCU_TRAFFIC_LENS_1E7 = 13.2e6            # four segment launches + tail: 3.52 + 2.78 + 2.42 + 2.25 + 2.21 MB read
 NCU_TRAFFIC_WALK_1E7 = 514.4e6 + 12.9e6
+# smsp__inst_executed_pipe_fp64.sum over the launches of one 1e7-molecule step (walk + 4 segments + tail), ncu
+NCU_FP64_WARP_INST_STEP_1E7 = 1.2646e8     # profiles/r02_fp64_inst.csv: 0.64 (walk) + 40.47 + 31.83 + 27.62 + 25.77 (segments) + 0.13 (tail) million
 # algorithmic work per unit
 FLOP_PER_ROW = 30      # one ballistic step + hit test
 FLOP_PER_STEP = 162    # one lens RK step (4 force evaluations)
 BYTES_PER_MOLECULE = 49  # IC replay: 6 x 8 B read + 1 B fate written
+
+
+N_PER_STEP = 10_000_000   # molecules per GPU per step of the GPU arm (configs[1])
+
+
+def shared_config(n=N_PER_STEP):
+    """The same dict from both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "molecules_per_step_per_gpu": int(n),
+            "inputs": "SoA FP64 initial conditions resident in HBM (480 MB per 1e7 molecules, larger than the 126 MB L2: no flush needed)",
+            "outputs": "fate byte per molecule + per-fate Counter (+ NCCL all-reduce of the Counter when n_gpus > 1)",
+            "sharding": "independent molecules, contiguous global-index block per rank"}
+
+
+def reference_python(cores: int):
+    """The UNMODIFIED reference (baseline/_ref, installed by baseline/install_ref.sh) timed on the host cores:
+    run_simulation(n_jobs=cores) and run_simulation(n_jobs=1) on the lens beamline with the same injected table
+    (BASELINE.md section 3).  Runs in a subprocess: its package is also called `trajectories`."""
+    import subprocess
+    import tempfile
+
+    ref = ROOT / "baseline" / "_ref"
+    if not (ref / "trajectories" / "trajectory_simulator.py").exists():
+        return {"unavailable": "baseline/_ref is empty (run baseline/install_ref.sh where /root/reference exists)"}
+    from trajectories.centrex import lens_table
+
+    r, a = lens_table()
+    with tempfile.TemporaryDirectory() as td:
+        np.savez(os.path.join(td, "table.npz"), r=r, a=a)
+        env = dict(os.environ, PYTHONPATH=f"{ref}:{ROOT / 'oracle' / 'stubs'}")
+        for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+            env[k] = "1"                      # one process per core through joblib, like the reference's users
+        cmd = [sys.executable, str(ROOT / "baseline" / "run_reference.py"), os.path.join(td, "table.npz"),
+               str(8000 * cores), str(cores), "20000", "1"]
+        try:
+            out = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=td, timeout=600)
+        except subprocess.TimeoutExpired:
+            return {"unavailable": "reference run exceeded 600 s"}
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("REFERENCE_JSON ")]
+    if out.returncode != 0 or not lines:
+        return {"unavailable": "reference run failed: " + (out.stderr.strip().splitlines() or ["?"])[-1][:200]}
+    runs = json.loads(lines[-1][len("REFERENCE_JSON "):])
+    return {"what": "otimgren/centrex-molecule-trajectories, unmodified, TrajectorySimulator.run_simulation on the lens beamline "
+                    "(wall clock incl. sampling and the joblib pool); matplotlib/h5py/hexalattice/centrex_TlF stubbed, lens table injected",
+            "all_cores": {"value": runs[0]["molecules_per_s"], "unit": UNIT, "cores": runs[0]["n_jobs"], "n": runs[0]["molecules"],
+                          "seconds": runs[0]["seconds"]},
+            "one_core": {"value": runs[1]["molecules_per_s"], "unit": UNIT, "cores": 1, "n": runs[1]["molecules"],
+                         "seconds": runs[1]["seconds"]}}
 
 
 def build_workload():
@@ -108,12 +157,16 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = args.steps * per_step / dt
     sample = f"{per_step} molecules per step (bounded sample of the 1e7-molecule step), Philox source + propagation + Counter"
+    # the reference itself (pure Python) on the same cores, reported beside the port; the port stays the arm's
+    # value: it is ~2000x faster than the reference and therefore the harder baseline
+    ref_py = None if args.no_reference_python else reference_python(threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "molecules_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": shared_config(), "sample_molecules_per_step": per_step,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "reference_python": ref_py},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -240,6 +293,8 @@ def run_ours(args):
     work = work1
 
     # ---- pass A: K steps back to back on one stream, every kernel timed with CUDA events ----
+    sampler = ClockSampler(local)          # NVML start-up takes a rank-dependent time: keep it ahead of the barriers
+    sampler.start()                        # SM clock and throttle reasons are sampled through passes A and B
     barrier()
     lib.cmt_timing_enable(1)
     lib.cmt_timing_read(None, None, 1)
@@ -276,10 +331,8 @@ def run_ours(args):
     for k in range(warm):
         step(slots[k % len(slots)])
     prop.join()
-    sampler = ClockSampler(local)          # NVML start-up takes a rank-dependent time: keep it ahead of the barrier
     prop.reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
     barrier()
     e0.record()
     for k in range(args.steps):
@@ -363,17 +416,35 @@ def run_ours(args):
     flop_rows = FLOP_PER_ROW * float(work[0])
     lens_tflops = flop_lens / (lens_ms * 1e-3) / 1e12 if lens_ms > 0 else None
     fp64_peak_tflops = 2 * dfma.value / 1e12       # FMA = 2 flop
+    step_ms = ms / args.steps
+    lens_tflops_overlapped = flop_lens / (step_ms * 1e-3) / 1e12
+    # FP64 pipe time of one step from the instruction counts ncu reports for the same launches (they do not depend
+    # on how launches overlap): warp instructions on the FP64 pipe x 2 issue cycles / (SMs x 4 sub-partitions)
+    sm_mhz = (torch.cuda.get_device_properties(local).clock_rate / 1e3)
+    fp64_cycles = NCU_FP64_WARP_INST_STEP_1E7 * (n / 1e7) * 2 / (prop.dev_sm_count() * 4)
     roofline = {
-        "kernel": "lens_seg_kernel (the lens stage of one step: 4 segment launches of 150 RK steps + tail_kernel)", "bound": "fp64", "achieved": lens_tflops, "peak": fp64_peak_tflops,
-        "unit": "TFLOP/s", "frac": (lens_tflops / fp64_peak_tflops) if lens_tflops else None,
+        "kernel": "lens_seg_kernel (the RK integrator of the ElectrostaticLens: 4 segment launches of 150 steps per step)",
+        "regime": "overlapped: pass B, the headline -- consecutive steps on alternating streams, so the lens stage of one step runs "
+                  "beside the walk kernel and the lens stages of its neighbours; a step then takes ms_per_step of device time",
+        "bound": "fp64", "achieved": lens_tflops_overlapped, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
+        "frac": lens_tflops_overlapped / fp64_peak_tflops,
+        "algorithmic_flop_per_launch": flop_lens, "avg_launch_ms": step_ms,
+        "avg_launch_ms_note": "device time per step in the overlapped pass (CUDA events around the K steps / K): kernels of different steps "
+                              "overlap, so a per-kernel duration does not exist in this regime; the lone durations are in roofline_one_stream",
+        "fp64_pipe_busy": fp64_cycles / (step_ms * 1e-3 * sm_mhz * 1e6),
+        "fp64_pipe_busy_source": "derived: smsp__inst_executed_pipe_fp64.sum of one step's launches (ncu, profiles/r02_*) x 2 cycles per warp "
+                                 "instruction / (592 sub-partitions x SM clock x ms_per_step)",
         "traffic": NCU_TRAFFIC_LENS_1E7 * n / 1e7, "traffic_source": "profiles/r01_full_f_segments.txt (ncu --set full, summed over the stage's launches)",
-        "fp64_pipe_utilisation_ncu": {"segment_1": 0.631, "segment_2": 0.586, "segment_3": 0.552, "segment_4": 0.525,
-                                      "at_8e7_molecules_per_launch": 0.695},
         "peak_source": "measured live: cmt_fp64_peak DFMA stream (no FP64 figure in MEASURED_PEAKS.json)",
+        "dadd_peak_tops": dadd.value / 1e12,
+    }
+    roofline_one_stream = {
+        "kernel": "lens_seg_kernel x 4 + tail_kernel (the lens stage of one step)", "regime": "one stream: pass A, nothing overlapped",
+        "bound": "fp64", "achieved": lens_tflops, "peak": fp64_peak_tflops,
+        "unit": "TFLOP/s", "frac": (lens_tflops / fp64_peak_tflops) if lens_tflops else None,
         "algorithmic_flop_per_launch": flop_lens, "avg_launch_ms": lens_ms,
         "share_of_step": lens_ms / (ms_seq / args.steps) if ms_seq > 0 else None,
         "timed_in": "pass A: the same K steps back to back on one stream (kernels not overlapped), CUDA events around the lens stage of every step",
-        "dadd_peak_tops": dadd.value / 1e12,
     }
     walk_gbs = BYTES_PER_MOLECULE * n / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else None
     roofline_walk = {
@@ -409,6 +480,18 @@ def run_ours(args):
     barrier()
     e2e_value = world * n * args.steps / e2e_s
     e2e_ok = bool((cnt_host == counters).all()) if world == 1 else None
+    # what the host link delivers for the same pinned buffer (one cudaMemcpyAsync of all six components)
+    scratch = torch.empty_like(ic)
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best_h2d = 0.0
+    for _ in range(4):
+        h0.record()
+        scratch.copy_(ic_host, non_blocking=True)
+        h1.record()
+        torch.cuda.synchronize()
+        best_h2d = max(best_h2d, ic_host.numel() * 8 / (h0.elapsed_time(h1) * 1e-3) / 1e9)
+    del scratch
+    e2e_gbs = (48 * n + n) * args.steps / e2e_s / 1e9
 
     # ---- e2e_philox: the run_simulation default path (device source, Counter back) ----
     def philox_step():
@@ -451,20 +534,20 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_rate(bl, vdist, xdist, target_s=12.0)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": f"{r['n']} molecules of the same workload ({r['seconds']:.1f} s): Philox source + propagation + Counter, oracle/cmt_oracle.c with OpenMP"}
+               "sample": f"{r['n']} molecules of the same workload ({r['seconds']:.1f} s): Philox source + propagation + Counter, oracle/cmt_oracle.c with OpenMP",
+               "reference_python": None if args.no_reference_python else reference_python(r["cores"])}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "molecules_per_step_per_gpu": n,
-                       "inputs": "SoA FP64 initial conditions resident in HBM (480 MB per 1e7 molecules, larger than the 126 MB L2: no flush needed)",
-                       "outputs": "fate byte per molecule + per-fate Counter (+ NCCL all-reduce of the Counter when n_gpus > 1)",
-                       "sharding": "independent molecules, contiguous global-index block per rank"},
+            "config": shared_config(n),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": n + 8 * (len(cnt_host) + 4),
                     "path": "cmt_run_host_ic: pinned host ICs -> H2D (2 streams, 2^21-molecule chunks) -> kernels -> fates + Counter D2H",
-                    "counters_match_device_run": e2e_ok},
+                    "counters_match_device_run": e2e_ok,
+                    "roofline": {"bound": "pcie", "achieved": e2e_gbs, "peak": best_h2d, "unit": "GB/s", "frac": e2e_gbs / best_h2d if best_h2d else None,
+                                 "peak_source": "measured live: one pinned-host to device copy of the step's 480 MB, best of 4 (per rank)"}},
             "e2e_philox": {"value": philox_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * (len(cnt_host) + 4),
                            "path": "cmt_run_host_philox (run_simulation default): Philox4x32-10 source on device, Counter D2H",
                            "counters_match_device_run": philox_same},
@@ -477,7 +560,7 @@ def run_ours(args):
             "value_one_stream": value_seq, "ms_per_step_one_stream": ms_seq / args.steps,
             "overlap": "none" if args.no_overlap else f"{prop.n_slots} streams: consecutive steps alternate streams (independent batches)"
                        + ("" if graphs is None else "; each step replays a CUDA graph (memset + walk + lens segments + tail)"),
-            "roofline": roofline, "roofline_walk": roofline_walk,
+            "roofline": roofline, "roofline_one_stream": roofline_one_stream, "roofline_walk": roofline_walk,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "counters": dict(zip(prop.flat.fate_names, counters.tolist())),
@@ -498,8 +581,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--molecules", type=float, default=1e7, help="molecules per GPU per step")
+    ap.add_argument("--molecules", type=float, default=N_PER_STEP, help="molecules per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-reference-python", action="store_true", help="skip timing the unmodified Python reference (baseline/_ref)")
     ap.add_argument("--no-overlap", action="store_true", help="issue every step on one stream")
     ap.add_argument("--no-contracted", action="store_true", help="skip the contracted-arithmetic pass")
     ap.add_argument("--slots", type=int, default=4, help="streams the overlapped steps alternate over")

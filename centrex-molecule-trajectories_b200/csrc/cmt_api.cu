@@ -92,6 +92,8 @@ struct PlaneD {
     double e[4];     // box: x1, x2, y1, y2
 };
 
+struct HostPipe;
+
 struct cmt_beamline {
     Params P;
     int device;
@@ -102,6 +104,11 @@ struct cmt_beamline {
     size_t tab_bytes;   // dynamic shared memory the lens/trajectory kernels need
     bool has_mesh;      // a Honeycomb is present: launch the kernel variants that carry its hit test
     std::vector<struct PlaneD> planes;   // the filter planes in binary64 (thresholds of the quick filter derive from them)
+    // staging of the host-buffer entry points: streams, device buffers, workspace.  Owned by the handle, so
+    // handles on different devices (or two handles on one device) never share or thrash a pipe; calls on ONE
+    // handle are serialised by pipe_mu.
+    std::mutex pipe_mu;
+    HostPipe *pipe = nullptr;
 };
 
 // Largest double s with sqrt(s) <= R under round-to-nearest, so that the
@@ -471,25 +478,39 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
         }
         P.tab = bl->d_tab;
         if (bl->tab_bytes > 40 * 1024) {
-            cudaFuncSetAttribute(lens_seg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
-            cudaFuncSetAttribute(lens_seg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
-            cudaFuncSetAttribute(tail_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
-            cudaFuncSetAttribute(tail_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
-            cudaFuncSetAttribute(tail_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
-            cudaFuncSetAttribute(tail_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
-            cudaFuncSetAttribute(trajectory_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
-            cudaFuncSetAttribute(trajectory_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
-            cudaFuncSetAttribute(crossing_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
-            cudaFuncSetAttribute(crossing_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl->tab_bytes);
+            // Tables beyond the default 48 KB of dynamic shared memory need the opt-in.  The attribute is per
+            // kernel and per device and must cover EVERY live handle, so it is only ever raised.
+            static std::mutex mu;
+            static size_t granted[64] = {0};
+            std::lock_guard<std::mutex> lk(mu);
+            if (device < 64 && bl->tab_bytes > granted[device]) {
+                const int b = (int)bl->tab_bytes;
+                cudaError_t a = cudaSuccess;
+                auto opt_in = [&](const void *fn) { if (a == cudaSuccess) a = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, b); };
+                opt_in((const void *)lens_seg_kernel<false>);   opt_in((const void *)lens_seg_kernel<true>);
+                opt_in((const void *)tail_kernel<false, false>); opt_in((const void *)tail_kernel<false, true>);
+                opt_in((const void *)tail_kernel<true, false>);  opt_in((const void *)tail_kernel<true, true>);
+                opt_in((const void *)trajectory_kernel<false>); opt_in((const void *)trajectory_kernel<true>);
+                opt_in((const void *)crossing_kernel<false>);   opt_in((const void *)crossing_kernel<true>);
+                if (a != cudaSuccess) {
+                    cudaFree(bl->d_tab);
+                    delete bl;
+                    return fail(CMT_ECUDA, "shared-memory opt-in for %d B of lens tables failed: %s", b, cudaGetErrorString(a));
+                }
+                granted[device] = bl->tab_bytes;
+            }
         }
     }
     *out = bl;
     return CMT_OK;
 }
 
+static void pipe_destroy(HostPipe *p);
+
 extern "C" void cmt_beamline_destroy(cmt_beamline_t *bl)
 {
     if (!bl) return;
+    pipe_destroy(bl->pipe);
     if (bl->d_tab) {
         DeviceGuard guard(bl->device);
         cudaFree(bl->d_tab);
@@ -637,24 +658,38 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
     memset(&S, 0, sizeof(S));
     if (src) S = *src;
 
-    const int64_t tiles = (n + WALK_THREADS - 1) / WALK_THREADS;
-    // Walk CTAs per SM: all thread slots for the Philox source (issue-bound); 14 when the initial conditions
-    // stream from HBM (72 registers with the next tile's loads in flight: 14 CTAs of 64 threads are resident)
+    // pair mode of the walk kernel (two molecules per thread and turn): all-circular front end with constant
+    // thresholds, Counter within the per-lane columns, no saved-index list, and -- for replayed initial
+    // conditions -- components that can be read as aligned 16-byte pairs
+    const bool pair_mode = bl->P.filt.n > 0 && bl->P.quick.usable && bl->P.quick.all_circles && !out->final_state &&
+                           !out->saved_index && bl->P.n_fates <= PAIR_MAX_FATES &&
+                           !(bl->P.flags & (CMT_FLAG_NO_FILTER | CMT_FLAG_NO_QUICK | CMT_FLAG_NO_PAIRS)) &&
+                           (philox || ((reinterpret_cast<uintptr_t>(ic) & 15u) == 0 && (ic_ld & 1) == 0));
+    const int per_tile = pair_mode ? 2 * WALK_THREADS : WALK_THREADS;
+    const int64_t tiles = (n + per_tile - 1) / per_tile;
     static const int tune_walk_ctas = env_int("CMT_TUNE_WALK_CTAS", 0);   // experiments only
     static const int tune_lens_prio = env_int("CMT_TUNE_LENS_PRIO", 1);
-    const int walk_ctas = tune_walk_ctas > 0 ? tune_walk_ctas : (philox ? 2048 : 896) / WALK_THREADS;
-    const int grid_walk = (int)std::min<int64_t>(tiles, (int64_t)bl->n_sm * walk_ctas);
     {
         ScopedTimer tm(0, st);
         // variants: source (replay / Philox) x arithmetic (exact / contracted) x Honeycomb test compiled in
         using WalkFn = void (*)(const Params, const cmt_source_t, uint64_t, const double *, int64_t, int64_t, int64_t,
-                                const cmt_outputs_t, Queue);
+                                const cmt_outputs_t, Queue, int);
         static const WalkFn walk[2][2][2] = {
             {{walk_kernel<false, false, false>, walk_kernel<false, false, true>},
              {walk_kernel<false, true, false>, walk_kernel<false, true, true>}},
             {{walk_kernel<true, false, false>, walk_kernel<true, false, true>},
              {walk_kernel<true, true, false>, walk_kernel<true, true, true>}}};
         const bool contract = bl->math == CMT_MATH_CONTRACTED;
+        // Persistent grid: as many CTAs per SM as the variant's registers allow (one wave, every CTA loops over
+        // tiles), capped at 14 for the one-molecule-per-thread replay form, whose prefetch was tuned there.
+        const WalkFn fn = walk[philox][contract][bl->has_mesh];
+        int walk_ctas = tune_walk_ctas;
+        if (walk_ctas <= 0) {
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&walk_ctas, fn, WALK_THREADS, 0));
+            if (!philox && !pair_mode) walk_ctas = std::min(walk_ctas, 14);
+            walk_ctas = std::max(walk_ctas, 1);
+        }
+        const int grid_walk = (int)std::min<int64_t>(tiles, (int64_t)bl->n_sm * walk_ctas);
         cudaLaunchConfig_t wcfg;
         memset(&wcfg, 0, sizeof(wcfg));
         wcfg.gridDim = dim3(grid_walk); wcfg.blockDim = dim3(WALK_THREADS);
@@ -663,12 +698,14 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
             // the quick filter's thresholds depend on the source's error bounds: per launch, by value
             Params P = bl->P;
             build_quick(bl->planes, bl->P.g, &S, P.quick);
+            // the constant thresholds of a Philox launch must again be all-circular and usable for pair mode
+            const int pm = pair_mode && P.quick.usable && P.quick.all_circles;
             CUDA_TRY(cudaLaunchKernelEx(&wcfg, walk[1][contract][bl->has_mesh], P, S, seed, (const double *)nullptr,
-                                        (int64_t)0, n, first_index, *out, Q));
+                                        (int64_t)0, n, first_index, *out, Q, pm));
         } else {
             CUDA_TRY(cudaLaunchKernelEx(&wcfg, walk[philox][contract][bl->has_mesh], bl->P, S, seed,
                                         philox ? (const double *)nullptr : ic, philox ? (int64_t)0 : ic_ld, n,
-                                        first_index, *out, Q));
+                                        first_index, *out, Q, (int)pair_mode));
         }
         count_launch();
     }
@@ -753,7 +790,10 @@ extern "C" int cmt_philox_draw(const cmt_source_t *src, uint64_t seed, int64_t f
         return fail(CMT_EINVAL, "unknown pos_kind %d", src->pos_kind);
     if (n == 0) return CMT_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    int dev = 0, n_sm = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)n_sm * 16);
     {
         ScopedTimer tm(3, st);
         draw_kernel<<<grid, 256, 0, st>>>(*src, seed, first_index, index, n, ic, ic_ld);
@@ -835,8 +875,6 @@ extern "C" int cmt_plane_crossings(const cmt_beamline_t *bl, int64_t n, const do
 // caller's buffers (truly asynchronous when those are pinned, still correct
 // when they are pageable).  H2D of chunk k+1 overlaps the kernels of chunk k.
 // ---------------------------------------------------------------------------
-namespace {
-
 struct HostPipe {
     int device = -1;
     int64_t chunk = 0;
@@ -864,8 +902,22 @@ struct HostPipe {
     ~HostPipe() { release(); }
 };
 
-std::mutex g_pipe_mu;
-HostPipe g_pipe;
+static void pipe_destroy(HostPipe *p) { delete p; }
+
+namespace {
+
+int pipe_allocate(HostPipe &p, int64_t chunk, bool keep_ic, bool keep_fate, bool keep_final)
+{
+    for (int k = 0; k < 2; ++k) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&p.st[k], cudaStreamNonBlocking));
+        CUDA_TRY(cudaMalloc(&p.d_ws[k], p.ws_bytes));
+        if (keep_ic) CUDA_TRY(cudaMalloc(&p.d_ic[k], (size_t)6 * chunk * sizeof(double)));
+        if (keep_fate) CUDA_TRY(cudaMalloc(&p.d_fate[k], (size_t)chunk));
+        if (keep_final) CUDA_TRY(cudaMalloc(&p.d_final[k], (size_t)10 * chunk * sizeof(double)));
+    }
+    CUDA_TRY(cudaMalloc(&p.d_cnt, (CMT_MAX_FATES + CMT_WORK_SLOTS) * sizeof(int64_t)));
+    return CMT_OK;
+}
 
 int pipe_prepare(HostPipe &p, const cmt_beamline_t *bl, int64_t chunk, bool want_ic, bool want_fate, bool want_final)
 {
@@ -879,15 +931,14 @@ int pipe_prepare(HostPipe &p, const cmt_beamline_t *bl, int64_t chunk, bool want
     p.device = bl->device;
     p.chunk = chunk;
     p.ws_bytes = std::max(ws, cmt_workspace_bytes(bl, chunk));
-    for (int k = 0; k < 2; ++k) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&p.st[k], cudaStreamNonBlocking));
-        CUDA_TRY(cudaMalloc(&p.d_ws[k], p.ws_bytes));
-        if (keep_ic) CUDA_TRY(cudaMalloc(&p.d_ic[k], (size_t)6 * chunk * sizeof(double)));
-        if (keep_fate) CUDA_TRY(cudaMalloc(&p.d_fate[k], (size_t)chunk));
-        if (keep_final) CUDA_TRY(cudaMalloc(&p.d_final[k], (size_t)10 * chunk * sizeof(double)));
+    const int rc = pipe_allocate(p, chunk, keep_ic, keep_fate, keep_final);
+    if (rc != CMT_OK) {
+        // nothing half-allocated survives a failure: the next call starts from scratch
+        p.release();
+        p.chunk = 0;
+        p.ws_bytes = 0;
     }
-    CUDA_TRY(cudaMalloc(&p.d_cnt, (CMT_MAX_FATES + CMT_WORK_SLOTS) * sizeof(int64_t)));
-    return CMT_OK;
+    return rc;
 }
 
 int pipe_collect(HostPipe &p, const cmt_beamline_t *bl, int64_t *counters_host, int64_t *work_host)
@@ -910,10 +961,12 @@ extern "C" int cmt_run_host_ic(const cmt_beamline_t *bl, int64_t n, const double
     if (!counters_host) return fail(CMT_EINVAL, "counters_host is NULL");
     if (n == 0) return CMT_OK;
     if (!ic_host) return fail(CMT_EINVAL, "ic_host is NULL");
-    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    cmt_beamline_t *owner = const_cast<cmt_beamline_t *>(bl);          // the pipe is a cache, not part of the beamline's value
+    std::lock_guard<std::mutex> lk(owner->pipe_mu);
     DeviceGuard guard(bl->device);
     CUDA_TRY(guard.status);
-    HostPipe &p = g_pipe;
+    if (!owner->pipe) owner->pipe = new HostPipe();
+    HostPipe &p = *owner->pipe;
     const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 21);
     int rc = pipe_prepare(p, bl, chunk, true, fate_host != nullptr, final_host != nullptr);
     if (rc) return rc;
@@ -952,10 +1005,12 @@ extern "C" int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t 
     if (n < 0) return fail(CMT_EINVAL, "n < 0");
     if (!counters_host || !src) return fail(CMT_EINVAL, "NULL argument");
     if (n == 0) return CMT_OK;
-    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    cmt_beamline_t *owner = const_cast<cmt_beamline_t *>(bl);
+    std::lock_guard<std::mutex> lk(owner->pipe_mu);
     DeviceGuard guard(bl->device);
     CUDA_TRY(guard.status);
-    HostPipe &p = g_pipe;
+    if (!owner->pipe) owner->pipe = new HostPipe();
+    HostPipe &p = *owner->pipe;
     // One chunk per 2^26 molecules (8.6 GB of queue workspace per stream), consecutive chunks on
     // alternating streams.  A run that fits one chunk is cut in two halves, one per stream, so that the
     // walk kernel of the second half overlaps the lens segments of the first (1e7 molecules: 1.32e10 ->
@@ -997,7 +1052,9 @@ extern "C" int cmt_selftest(int device, int64_t n, uint64_t seed, int mode, int6
     unsigned long long *d = nullptr;
     CUDA_TRY(cudaMalloc(&d, 5 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMemset(d, 0, 5 * sizeof(unsigned long long)));
-    selftest_kernel<<<148 * 8, 256>>>(n, seed, mode, d);
+    int n_sm = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    selftest_kernel<<<n_sm * 8, 256>>>(n, seed, mode, d);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     unsigned long long h[5] = {0, 0, 0, 0, 0};

@@ -181,23 +181,39 @@ __device__ __forceinline__ void walk_exact(const Params &P, const cmt_source_t &
 // retire at once, the others -- survivors bound for the lens and near misses of an edge -- are
 // parked in a per-warp shared-memory ring and walked in binary64 32 at a time, on full warps.
 // The filter needs nothing but fates, so it is skipped when final rows are requested.
+//
+// Pair mode (the common case: all-circular front end, constant thresholds, no saved-index list): a thread
+// judges TWO adjacent molecules per turn.  Replayed initial conditions arrive as one 16-byte load per
+// component and thread (LDG.E.128: a warp reads 512 contiguous bytes per component), the two parabolas are
+// evaluated with packed single-precision instructions (quick_fate2), both fate bytes leave in one 16-bit
+// store, and the Counter is kept in a per-lane column of shared memory (no atomics, no warp matching) that is
+// folded into the block's histogram once, at the end.
+constexpr int WALK_RING = 96;          // parked molecules per warp: fewer than 32 before a turn, at most 64 more after it
+constexpr int PAIR_MAX_FATES = 16;     // fates the per-lane Counter columns cover (4 KB of shared memory per CTA)
+
 template <bool PHILOX, bool CONTRACT, bool MESH>
 __global__ void __launch_bounds__(WALK_THREADS)
 walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source_t S, uint64_t seed,
             const double *__restrict__ ic, int64_t ic_ld, int64_t n, int64_t first_index,
-            const __grid_constant__ cmt_outputs_t O, Queue Q)
+            const __grid_constant__ cmt_outputs_t O, Queue Q, int pair_mode)
 {
     __shared__ BlockAcc acc;
-    __shared__ int64_t ring[WALK_THREADS / 32][64];
+    __shared__ int64_t ring[WALK_THREADS / 32][WALK_RING];
+    __shared__ unsigned lane_hist[PAIR_MAX_FATES][WALK_THREADS];
     block_acc_init(acc);
 
     const int n_walk = P.first_lens < P.n_el ? P.first_lens + 1 : P.n_el;
-    const int64_t n_tiles = (n + WALK_THREADS - 1) / WALK_THREADS;
     const bool filt = P.filt.n > 0 && O.final_state == nullptr && !(P.flags & CMT_FLAG_NO_FILTER);
     const bool quick = P.quick.usable && !(P.flags & CMT_FLAG_NO_QUICK);
+    const bool pairs = pair_mode != 0 && filt && quick;
+    const int per_tile = pairs ? 2 * WALK_THREADS : WALK_THREADS;
+    const int64_t n_tiles = (n + per_tile - 1) / per_tile;
     unsigned rows_total = 0, entries = 0, filtered = 0;
     int64_t *my_ring = ring[threadIdx.x >> 5];
     int pending = 0;                                  // warp-uniform
+    if (pairs) {
+        for (int f = 0; f < PAIR_MAX_FATES; ++f) lane_hist[f][threadIdx.x] = 0;     // own column only
+    }
 
     // One turn of the loop either judges a fresh tile in FP32 or walks up to 32 parked molecules in
     // binary64 (a single call site of walk_exact keeps the kernel small).  Everything that steers
@@ -205,12 +221,25 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
     int64_t tile = blockIdx.x;
     // Replay mode: the initial conditions of the NEXT tile are requested before the current tile is
     // judged, so that the HBM latency overlaps the filter instead of stalling the warp at each tile.
-    double pre[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    auto prefetch = [&](int64_t t) {
-        const int64_t i = t * WALK_THREADS + threadIdx.x;
-        if (t < n_tiles && i < n) {
+    double2 pre[6];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) pre[c] = ic[c * ic_ld + i];
+    for (int c = 0; c < 6; ++c) pre[c] = make_double2(0.0, 0.0);
+    auto prefetch = [&](int64_t t) {
+        if (pairs) {
+            const int64_t i = t * per_tile + 2 * threadIdx.x;
+            if (t < n_tiles && i + 1 < n) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) pre[c] = __ldg(reinterpret_cast<const double2 *>(ic + c * ic_ld + i));
+            } else if (t < n_tiles && i < n) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) pre[c] = make_double2(ic[c * ic_ld + i], 0.0);
+            }
+        } else {
+            const int64_t i = t * per_tile + threadIdx.x;
+            if (t < n_tiles && i < n) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) pre[c].x = ic[c * ic_ld + i];
+            }
         }
     };
     if (!PHILOX && filt) prefetch(tile);
@@ -223,15 +252,53 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
             j = my_ring[pending + lane_id()];
             act = true;
             __syncwarp();
+        } else if (tile < n_tiles && pairs) {
+            const int64_t i = tile * per_tile + 2 * threadIdx.x;
+            const bool v0 = i < n, v1 = i + 1 < n;
+            tile += gridDim.x;
+            FiltIn2 q;
+            if (!PHILOX) {
+                q.x0 = f2(__double2float_rn(pre[0].x), __double2float_rn(pre[0].y));
+                q.y0 = f2(__double2float_rn(pre[1].x), __double2float_rn(pre[1].y));
+                q.z0 = f2(__double2float_rn(pre[2].x), __double2float_rn(pre[2].y));
+                q.vx = f2(__double2float_rn(pre[3].x), __double2float_rn(pre[3].y));
+                q.vy = f2(__double2float_rn(pre[4].x), __double2float_rn(pre[4].y));
+                q.vz = f2(__double2float_rn(pre[5].x), __double2float_rn(pre[5].y));
+                prefetch(tile);
+            } else {
+                const FiltIn a = draw_f32(S, seed, (uint64_t)(first_index + i));
+                const FiltIn b = draw_f32(S, seed, (uint64_t)(first_index + i + 1));
+                q.x0 = f2(a.x0, b.x0); q.y0 = f2(a.y0, b.y0); q.z0 = f2(a.z0, b.z0);
+                q.vx = f2(a.vx, b.vx); q.vy = f2(a.vy, b.vy); q.vz = f2(a.vz, b.vz);
+                q.ex0 = f2(a.ex0, b.ex0); q.ey0 = f2(a.ey0, b.ey0);
+                q.evx = f2(a.evx, b.evx); q.evy = f2(a.evy, b.evy); q.evz = f2(a.evz, b.evz);
+            }
+            int fate[2], rows[2];
+            quick_fate2<!PHILOX>(P.filt, P.quick, P.fate_detected, q, fate, rows);
+            const bool d0 = v0 && fate[0] >= 0, d1 = v1 && fate[1] >= 0;
+            if (O.fate) {
+                if (d0 && d1) *reinterpret_cast<uint16_t *>(O.fate + i) = (uint16_t)(fate[0] | (fate[1] << 8));
+                else if (d0) O.fate[i] = (uint8_t)fate[0];
+                else if (d1) O.fate[i + 1] = (uint8_t)fate[1];
+            }
+            if (d0) { ++lane_hist[fate[0]][threadIdx.x]; rows_total += rows[0]; ++filtered; }
+            if (d1) { ++lane_hist[fate[1]][threadIdx.x]; rows_total += rows[1]; ++filtered; }
+            const bool need0 = v0 && fate[0] < 0, need1 = v1 && fate[1] < 0;
+            const unsigned m0 = __ballot_sync(0xffffffffu, need0), m1 = __ballot_sync(0xffffffffu, need1);
+            const unsigned below = (1u << lane_id()) - 1u;
+            if (need0) my_ring[pending + __popc(m0 & below)] = i;
+            if (need1) my_ring[pending + __popc(m0) + __popc(m1 & below)] = i + 1;
+            pending += __popc(m0) + __popc(m1);
+            continue;
         } else if (tile < n_tiles) {
-            const int64_t i = tile * WALK_THREADS + threadIdx.x;
+            const int64_t i = tile * per_tile + threadIdx.x;
             const bool valid = i < n;
             tile += gridDim.x;
             if (filt) {
                 int fate = -1, rows = 0;
                 FiltIn q;
                 if (!PHILOX) {
-                    q = filter_input(pre[0], pre[1], pre[2], pre[3], pre[4], pre[5]);
+                    q = filter_input(pre[0].x, pre[1].x, pre[2].x, pre[3].x, pre[4].x, pre[5].x);
                     prefetch(tile);
                 }
                 if (valid) {
@@ -255,14 +322,24 @@ walk_kernel(const __grid_constant__ Params P, const __grid_constant__ cmt_source
             act = valid;
         } else if (pending > 0) {
             __syncwarp();
-            act = (int)lane_id() < pending;
-            j = act ? my_ring[lane_id()] : 0;
-            pending = 0;
+            act = (int)lane_id() < min(pending, 32);
+            j = act ? my_ring[max(pending - 32, 0) + lane_id()] : 0;
+            pending = max(pending - 32, 0);
+            __syncwarp();
         } else {
             break;
         }
         walk_exact<PHILOX, CONTRACT, MESH>(P, S, seed, ic, ic_ld, first_index, O, Q, acc, n_walk, j, act,
                                            rows_total, entries);
+    }
+    if (pairs) {
+        // fold the per-lane Counter columns into the block's histogram
+        __syncthreads();
+        for (int f = threadIdx.x; f < PAIR_MAX_FATES; f += blockDim.x) {
+            unsigned sum = 0;
+            for (int l = 0; l < WALK_THREADS; ++l) sum += lane_hist[f][(l + f) % WALK_THREADS];
+            if (sum) atomicAdd(&acc.hist[f], sum);
+        }
     }
     warp_add_work(acc, 0, rows_total);
     warp_add_work(acc, 3, entries);
@@ -295,7 +372,9 @@ constexpr int LENS_SEGMENT_STEPS = 150;   // RK steps per launch (measured: 75..
 constexpr int LENS_UNROLL = CMT_LENS_UNROLL;   // RK steps per trip of the segment loop
 constexpr int LENS_SEG_GRID_CTAS = 3;     // CTAs per SM one launch asks for: leaves room for the next step's walk CTAs
 #ifndef LENS_SEG_MIN_CTAS
-#define LENS_SEG_MIN_CTAS 5               // register budget: 96 per thread, nothing spilled inside the step loop
+#define LENS_SEG_MIN_CTAS 4               // register budget: 128 per thread (124 used): nothing spilled or rematerialised inside the
+                                          // step loop.  Measured against 5 (96 registers) and 6 (80) with the one-record RK step:
+                                          // lens stage 0.481 / 0.514 / 0.535 ms at 1e7 molecules, 2.55 / 2.81 / 2.94 ms at 8e7
 #endif
 
 template <bool CONTRACT>

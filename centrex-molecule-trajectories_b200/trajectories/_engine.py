@@ -169,7 +169,7 @@ def device_beamline(flat: FlatBeamline, device: int, math: str = "exact") -> Dev
     k = (flat.key, int(device), math)
     h = _handles.get(k)
     if h is None:
-        if len(_handles) > 64:
+        if len(_handles) > 256:
             _handles.clear()
         h = _handles[k] = DeviceBeamline(flat, device, math)
     return h
@@ -268,6 +268,36 @@ class Propagator:
         self.counters.zero_()
         self.work.zero_()
 
+    def rebind(self, flat: FlatBeamline):
+        """Point this launch context at another beamline with the same fates (a sweep point: same elements, another
+        lens table) and give it fresh Counter / work tensors; streams and workspaces are kept, and launches already
+        queued for the previous beamline keep their own handle and counters."""
+        if flat.fate_names != self.flat.fate_names:
+            raise ValueError("rebind needs a beamline with the same fates")
+        torch = _torch()
+        self.flat = flat
+        self.dev = device_beamline(flat, self.device, self.math)
+        self.counters = torch.zeros(len(flat.fate_names), dtype=torch.int64, device=self.tdev)
+        self.work = torch.zeros(8, dtype=torch.int64, device=self.tdev)
+
+    def release(self):
+        """Give the queue workspaces back to the allocator (8.6 GB per stream slot at the default chunk)."""
+        self.join()
+        _torch().cuda.current_stream(self.device).synchronize()
+        self._ws = [None] * (self.n_slots + 1)
+
+    def fit_chunk(self, chunk: int, fraction: float = 0.5) -> int:
+        """Largest launch size <= `chunk` whose workspaces (one per stream slot plus one, 128 B per molecule each, and
+        the saved-index buffer) fit into `fraction` of the device memory that is free right now."""
+        free, _total = _torch().cuda.mem_get_info(self.device)
+        held = sum(w.numel() for w in self._ws if w is not None)
+        per_molecule = (self.n_slots + 1) * 2 * 8 * 8 + 16
+        fit = int(fraction * (free + held)) // per_molecule
+        return max(1 << 20, min(int(chunk), fit))
+
+    def dev_sm_count(self) -> int:
+        return int(_torch().cuda.get_device_properties(self.device).multi_processor_count)
+
     # -- streams ---------------------------------------------------------------
     def _slot_stream(self, slot):
         torch = _torch()
@@ -290,12 +320,13 @@ class Propagator:
         def __enter__(self):
             torch = _torch()
             p = self.prop
+            self.caller = torch.cuda.current_stream(p.device)
             if self.slot is None:
                 self.index = p.n_slots
                 self.ctx = torch.cuda.device(p.device)
             else:
                 st = p._slot_stream(self.slot)
-                st.wait_stream(torch.cuda.current_stream(p.device))   # inputs produced on the caller's stream
+                st.wait_stream(self.caller)                           # inputs produced on the caller's stream
                 self.index = self.slot % p.n_slots
                 self.ctx = torch.cuda.stream(st)
             self.ctx.__enter__()
@@ -303,6 +334,14 @@ class Propagator:
 
         def __exit__(self, *exc):
             return self.ctx.__exit__(*exc)
+
+        def hand_over(self, *tensors):
+            """Outputs allocated on a slot stream are consumed on the caller's stream (after join()): tell the
+            caching allocator, so that their memory is not reused while the caller's work is still queued."""
+            if self.slot is not None:
+                for t in tensors:
+                    if t is not None:
+                        t.record_stream(self.caller)
 
     def _workspace(self, n: int, index: int):
         torch = _torch()
@@ -354,6 +393,7 @@ class Propagator:
             nat.check(nat.lib().cmt_propagate_ic(self.dev.handle, n, int(first_index), ic.data_ptr(), ic.stride(0),
                                                  C.byref(O), ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
             saved = self._finish_saved(save_mask, saved_buf, L.index)
+            L.hand_over(fate, final, saved)
         return PropagateResult(self.counters, self.work, fate, final, saved, self.flat.fate_names)
 
     def propagate_philox(self, source: nat.Source, seed: int, first_index: int, n: int, want_fate=False,
@@ -367,6 +407,7 @@ class Propagator:
                                                      int(first_index), int(n), C.byref(O), ws.data_ptr(),
                                                      ws.numel(), _stream_ptr(self.device)))
             saved = self._finish_saved(save_mask, saved_buf, L.index)
+            L.hand_over(fate, final, saved)
         return PropagateResult(self.counters, self.work, fate, final, saved, self.flat.fate_names)
 
     def capture_ic(self, ic, first_index=0, want_fate=True, slot=0) -> "GraphedStep":

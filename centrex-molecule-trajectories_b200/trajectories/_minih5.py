@@ -83,7 +83,8 @@ class _DatasetNode(_Node):
 
     @property
     def dtype(self):
-        return self._data.dtype if self._data is not None else self._lazy[3]
+        dt = np.dtype(self._data.dtype if self._data is not None else self._lazy[3])
+        return dt if dt.isnative else dt.newbyteorder("=")          # what load() returns
 
     def load(self) -> np.ndarray:
         if self._data is None:
@@ -360,6 +361,7 @@ class _Writer:
               + struct.pack("<QQII", 0, root["header"], 1, 0) + struct.pack("<QQ", root["levels"][-1][0], root["heap"]))
         assert len(sb) == 96
         tmp = f"{path}.tmp{os.getpid()}"
+        sources: Dict[str, object] = {}
         with open(tmp, "wb") as f:
             f.write(sb)
             pos = 96
@@ -369,6 +371,23 @@ class _Writer:
                     pos = addr
                 assert addr == pos, (addr, pos)
                 if isinstance(part, _DatasetNode):
+                    if part._data is None and np.dtype(part._lazy[3]).isnative:
+                        # untouched dataset of the file being rewritten: copy its bytes, one shared handle per source
+                        src_path, offset, shape, dtype = part._lazy
+                        src = sources.get(src_path)
+                        if src is None:
+                            src = sources[src_path] = open(src_path, "rb")
+                        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+                        src.seek(offset)
+                        left = nbytes
+                        while left:
+                            chunk = src.read(min(left, 1 << 24))
+                            if not chunk:
+                                raise OSError("source file truncated while copying a dataset")
+                            f.write(chunk)
+                            left -= len(chunk)
+                        pos += nbytes
+                        continue
                     arr = _contig(part.load())
                     if arr.dtype == np.bool_:
                         arr = arr.astype(np.int8)
@@ -379,6 +398,8 @@ class _Writer:
                     pos += len(part)
             if pos < eof:
                 f.write(b"\0" * (eof - pos))
+        for src in sources.values():
+            src.close()
         os.replace(tmp, path)
 
 

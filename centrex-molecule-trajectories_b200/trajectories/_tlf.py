@@ -41,14 +41,12 @@ def rigid_rotor_energies_hz(J: int, mJ: int, Ez_V_per_cm, j_max: int = J_MAX) ->
     jj = Js[:-1]
     off = np.sqrt(((jj + 1.0) ** 2 - m * m) / ((2.0 * jj + 1.0) * (2.0 * jj + 3.0)))
     Ez = np.atleast_1d(np.asarray(Ez_V_per_cm, dtype=np.float64))
-    out = np.empty(Ez.shape, dtype=np.float64)
     k = J - m  # no crossings inside one mJ block: the k-th eigenvalue stays the k-th
     H0 = np.diag(diag)
     C = np.diag(off, 1) + np.diag(off, -1)
-    for i, E in enumerate(Ez):
-        w = np.linalg.eigvalsh(H0 - D_TLF_HZ_PER_V_CM * E * C)
-        out[i] = w[k]
-    return out
+    # one stacked call: LAPACK diagonalises the matrices one after the other, as a Python loop over them would
+    H = H0[None, :, :] - (D_TLF_HZ_PER_V_CM * Ez.reshape(-1))[:, None, None] * C[None, :, :]
+    return np.linalg.eigvalsh(H)[:, k].reshape(Ez.shape)
 
 
 def rigid_rotor_stark_joule(J: int, mJ: int, Ez_V_per_cm) -> np.ndarray:

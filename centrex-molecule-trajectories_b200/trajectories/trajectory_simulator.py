@@ -220,7 +220,7 @@ class TrajectorySimulator:
                     torch.distributed.broadcast(s, 0)
                     seed = int(s.item())
             lo, hi = eng.shard_range(total, rank, world)
-            chunk = self.chunk
+            chunk = prop.fit_chunk(self.chunk)
             if not save_mask and (1 << 21) <= hi - lo <= chunk:
                 # a run that fits one chunk goes out as two halves on two streams: the walk kernel of the
                 # second overlaps the lens segments of the first (the result does not depend on the cut)
@@ -268,6 +268,7 @@ class TrajectorySimulator:
         counts = eng.allreduce_counts(prop.counters.clone()).cpu().numpy()
         work = eng.allreduce_counts(prop.work.clone()).cpu().numpy()
         self.last_work = work
+        prop.release()          # the queue workspaces go back to the allocator; the beamline handle stays cached
         if work[2] > 0:
             # the reference's interp1d raises for r beyond the table (bounds_error=True)
             raise ValueError(
@@ -287,6 +288,114 @@ class TrajectorySimulator:
 
     # the reference's README calls the parallel entry point by this name (README.md:52)
     run_simulation_parallel = run_simulation
+
+    def run_sweep(
+        self,
+        beamline: Beamline,
+        states,
+        voltages=None,
+        run_name: str = "J = {J}, mJ = {mJ}, V = {V:.0f}",
+        vdist=CeNTREXVelocityDistribution(),
+        xdist=CeNTREXPositionDistribution(),
+        N_traj: int = 1000,
+        apertures_of_interest=[],
+        n_jobs=1,
+        seed: Optional[int] = None,
+        lens_name: str = "ES lens",
+    ) -> dict:
+        """The loop of examples/lens_simulation_different_states.py:135-152 (set the lens' state, reset its table,
+        run, keep the result) over `states` x `voltages` as ONE batched call.
+
+        Every point is what `run_simulation(beamline, name, vdist, xdist, N_traj, apertures_of_interest, n_jobs, seed)`
+        gives after `lens.state = state; lens.V = V; lens.a_interp = None` -- same Counter, same saved molecules --
+        but the Stark tables of all points are built in one vectorised pass, the beamline is flattened once, and,
+        when no trajectories are asked for, the launches of consecutive points go out on alternating streams with a
+        single read-back of all Counters at the end.  All points use the same seed, i.e. the same molecules (common
+        random numbers: differences between points are differences of the lens, not of the sample).
+
+        `states`: objects with `find_largest_component()` (centrex_TlF states) or `(J, mJ)` pairs; `voltages`: None
+        keeps the lens' own voltage.  Returns `{(J, mJ, V): SimulationResult}`, also stored in `self.results` under
+        `run_name.format(J=, mJ=, V=)`; `self.counter` / `self.result` are those of the last point.
+        """
+        from copy import copy as shallow
+        from .stark_potential import state_quantum_numbers
+
+        torch = eng._torch()
+        lens = beamline.find_element(lens_name)
+        if lens is None:
+            raise ValueError(f"no element named {lens_name!r} in the beamline")
+        source = eng.make_source(vdist, xdist)
+        if source is None:
+            raise ValueError("run_sweep needs the built-in distributions (device source); loop over run_simulation otherwise")
+        Vs = [lens.V] if voltages is None else [float(v) for v in voltages]
+        points = [(state, V) for state in states for V in Vs]
+        N_loops = 100 * n_jobs
+        total = int(N_traj / N_loops) * N_loops
+        rank, world = eng.dist_info()
+        if seed is None:
+            seed = self.seed
+        if seed is None:
+            seed = int(eng.broadcast_object(int(np.random.randint(0, 2**62))))
+
+        # one flattening per point, differing only in the lens table
+        flats, keys, lenses = [], [], []
+        saved_state, saved_V, saved_tab = lens.state, lens.V, lens.a_interp
+        try:
+            for state, V in points:
+                lens.state, lens.V, lens.a_interp = state, V, None
+                flats.append(eng.flatten(beamline.elements))
+                J, mJ = state_quantum_numbers(state)
+                keys.append((J, mJ, V))
+                lenses.append((state, V, lens.a_interp))
+        finally:
+            lens.state, lens.V, lens.a_interp = saved_state, saved_V, saved_tab
+
+        prop = eng.Propagator(flats[0], self.device, math=self.math)
+        save_mask = flats[0].save_mask(list(apertures_of_interest))
+        lo, hi = eng.shard_range(total, rank, world)
+        chunk = prop.fit_chunk(self.chunk)
+        if not save_mask and (1 << 21) <= hi - lo <= chunk:
+            chunk = (hi - lo + 1) // 2
+        per_point, k = [], 0
+        for flat in flats:
+            prop.rebind(flat)
+            molecules: List[Molecule] = []
+            for first in range(lo, hi, chunk):
+                n = min(chunk, hi - first)
+                if not save_mask:
+                    prop.propagate_philox(source, seed, first, n, slot=k)
+                    k += 1
+                    continue
+                res = prop.propagate_philox(source, seed, first, n, save_mask=save_mask)
+                if res.saved_index.numel():
+                    molecules.extend(self._collect(prop, prop.draw(source, seed, index=res.saved_index)))
+            per_point.append((prop.counters, prop.work, molecules))
+        prop.join()
+        counts = eng.allreduce_counts(torch.stack([c for c, _, _ in per_point])).cpu().numpy()
+        works = eng.allreduce_counts(torch.stack([w for _, w, _ in per_point])).cpu().numpy()
+        self.last_work = works.sum(axis=0)
+        if works[:, 2].sum() > 0:
+            raise ValueError(f"A value in x_new is above the interpolation range ({int(works[:, 2].sum())} lens force "
+                             "evaluations fell outside the a_interp table)")
+        out = {}
+        for p, (key, flat) in enumerate(zip(keys, flats)):
+            counter = Counter()
+            for name, c in zip(flat.fate_names, counts[p]):
+                if c > 0:
+                    counter.increment_counter(name, int(c))
+            # each result carries its own beamline, with the lens as it was for that point
+            bl = shallow(beamline)
+            bl.elements = [shallow(e) if e is lens else e for e in beamline.elements]
+            pl = bl.elements[beamline.elements.index(lens)]
+            pl.state, pl.V, pl.a_interp = lenses[p]
+            molecules = per_point[p][2]
+            saved_counts = eng.gather_counts(len(molecules), prop.device) if world > 1 else [len(molecules)]
+            res = SimulationResult(counter, bl, xdist, vdist, molecules, sum(saved_counts[:rank]), sum(saved_counts))
+            out[key] = res
+            self.results[run_name.format(J=key[0], mJ=key[1], V=key[2])] = res
+            self.counter, self.result = counter, res
+        prop.release()
+        return out
 
     def plane_distributions(
         self,
@@ -386,7 +495,9 @@ class TrajectorySimulator:
         # each trajectory is a view of its slice of the result block
         mols = [from_rows(rows[lo[k]:lo[k + 1]], names[f], names[f] == "Detected")
                 for k, f in enumerate(np.asarray(fate).tolist())]
-        if rows.size and not np.isfinite(rows).all():
+        # (a non-finite value poisons every later row of its trajectory, so the last rows tell)
+        last = rows[np.asarray(lo[1:], dtype=np.int64) - 1] if len(lo) > 1 else rows[:0]
+        if last.size and not np.isfinite(last).all():
             # Beamline.propagate_through ends with trajectory.drop_nans() (beamline.py:38, molecule.py:160-167), which
             # also strips rows that a non-finite initial condition or an overflow filled with NaN / inf
             for m in mols:

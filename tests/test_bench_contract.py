@@ -21,12 +21,30 @@ def run(*args):
 
 
 def test_reference_arm_line():
-    d = run("--impl", "reference", "--steps", "1", "--warmup", "0")
+    d = run("--impl", "reference", "--steps", "1", "--warmup", "0", "--no-reference-python")
     assert COMMON <= set(d) and d["impl"] == "reference"
     assert d["unit"] == "molecules/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["value"] > 1e5 and d["dtype"] == "f64" and "workload" in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # both arms print the same `config` dict (the driver compares them)
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    assert d["config"] == bench.shared_config() and d["sample_molecules_per_step"] > 0
+
+
+def test_reference_python_leg():
+    """The unmodified reference (baseline/_ref) timed in a subprocess, when it has been installed."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    r = bench.reference_python(2)
+    if "unavailable" in r:
+        assert not (ROOT / "baseline" / "_ref" / "trajectories").exists()
+        pytest.skip(r["unavailable"])
+    assert r["all_cores"]["cores"] == 2 and r["all_cores"]["n"] == 16000 and 1e2 < r["all_cores"]["value"] < 1e6
+    assert r["one_core"]["cores"] == 1 and r["one_core"]["n"] == 20000 and 1e2 < r["one_core"]["value"] < 1e5
 
 
 @pytest.mark.gpu
@@ -39,6 +57,9 @@ def test_gpu_arm_line():
     for key in ("e2e", "e2e_philox", "e2e_api"):
         assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d[key]) and d[key]["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 48 * 2_000_000 and d["e2e"]["counters_match_device_run"] is True
+    assert d["roofline"]["regime"].startswith("overlapped") and d["roofline"]["avg_launch_ms"] <= d["ms_per_step"] * 1.0001
+    assert d["roofline_one_stream"]["regime"].startswith("one stream") and 0 < d["roofline"]["fp64_pipe_busy"] < 1
+    assert d["e2e"]["roofline"]["bound"] == "pcie" and 0 < d["e2e"]["roofline"]["frac"] <= 1.05
     for key in ("roofline", "roofline_walk"):
         r = d[key]
         assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r)

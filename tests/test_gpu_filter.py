@@ -128,6 +128,30 @@ def test_hostile_inputs(torch_cuda, cuda_lib):
         check_vs_oracle(torch_cuda, cuda_lib, bl, ic)
 
 
+@pytest.mark.parametrize("n", [1, 2, 63, 127, 128, 129, 100001])
+def test_pair_mode_edges_and_unaligned_inputs(torch_cuda, cuda_lib, n):
+    """Two molecules per thread: odd counts (the last thread holds one molecule), counts around a 128-molecule
+    tile, and initial conditions that cannot be read as aligned 16-byte pairs (odd leading dimension, a view that
+    starts at an odd column), which take the one-molecule form.  Fate by fate against the oracle."""
+    torch = torch_cuda
+    bl = lens_beamline(lens_table())
+    ic = standard_ics(n + 3, 50 + n % 7, 12.0)
+    want = oracle.propagate(bl.elements, ic)
+    prop = propagator(cuda_lib, bl.elements)
+    whole = torch.from_numpy(ic).cuda()                       # leading dimension n + 3
+    for lo, hi in ((0, n), (1, n + 1), (2, n + 2), (0, n + 3)):
+        prop.reset()
+        res = prop.propagate_ic(whole[:, lo:hi], want_fate=True)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(res.fate.cpu().numpy(), want["fate"][lo:hi])
+        np.testing.assert_array_equal(res.counters.cpu().numpy(), np.bincount(want["fate"][lo:hi], minlength=len(want["counters"])))
+    even = torch.from_numpy(np.ascontiguousarray(ic[:, : n + (n % 2)])).cuda()     # aligned, even leading dimension
+    prop.reset()
+    res = prop.propagate_ic(even[:, :n], want_fate=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(res.fate.cpu().numpy(), want["fate"][:n])
+
+
 def test_unusual_geometry(torch_cuda, cuda_lib):
     """Closed aperture (d = 0: thresholds the filter cannot use), offset rectangles, a field plate first,
     elements after a lens, more planes than the filter table holds."""
@@ -181,12 +205,15 @@ def test_filter_on_equals_filter_off_at_scale(torch_cuda, cuda_lib, math):
         src = eng.make_source(CeNTREXVelocityDistribution(), xdist)
         on, off = propagator(cuda_lib, bl.elements, 0, math), propagator(cuda_lib, bl.elements, 2, math)
         slow = propagator(cuda_lib, bl.elements, 4, math)      # per-molecule tolerances only
+        single = propagator(cuda_lib, bl.elements, 8, math)    # constant thresholds, one molecule per thread (no pairs)
         # Philox source
         a = on.propagate_philox(src, 99, 1 << 35, n, want_fate=True)
         fa, ca, wa = a.fate.clone(), a.counters.clone(), a.work.clone()
         b = off.propagate_philox(src, 99, 1 << 35, n, want_fate=True)
         c = slow.propagate_philox(src, 99, 1 << 35, n, want_fate=True)
+        d = single.propagate_philox(src, 99, 1 << 35, n, want_fate=True)
         torch.cuda.synchronize()
+        assert torch.equal(fa, d.fate) and torch.equal(ca, d.counters) and torch.equal(wa[:6], d.work[:6])
         assert torch.equal(fa, b.fate) and torch.equal(ca, b.counters)
         assert torch.equal(fa, c.fate) and torch.equal(ca, c.counters)
         assert torch.equal(wa[:5], b.work[:5]) and torch.equal(wa[:5], c.work[:5])
@@ -194,11 +221,13 @@ def test_filter_on_equals_filter_off_at_scale(torch_cuda, cuda_lib, math):
         assert int(c.work[5]) >= min_filtered * n and int(c.work[5]) >= int(wa[5])
         # replayed initial conditions
         ic = on.draw(src, 99, 1 << 35, n)
-        on.reset(), off.reset(), slow.reset()
+        on.reset(), off.reset(), slow.reset(), single.reset()
         a = on.propagate_ic(ic, want_fate=True)
         b = off.propagate_ic(ic, want_fate=True)
         c = slow.propagate_ic(ic, want_fate=True)
+        d = single.propagate_ic(ic, want_fate=True)
         torch.cuda.synchronize()
+        assert torch.equal(a.fate, d.fate) and torch.equal(a.counters, d.counters) and torch.equal(a.work[:6], d.work[:6])
         assert torch.equal(a.fate, b.fate) and torch.equal(a.counters, b.counters)
         assert torch.equal(a.fate, c.fate) and torch.equal(a.counters, c.counters)
         assert torch.equal(a.fate, fa)                     # and the same as the Philox run
@@ -206,9 +235,10 @@ def test_filter_on_equals_filter_off_at_scale(torch_cuda, cuda_lib, math):
         assert int(a.work[5]) >= (min_filtered - 0.005) * n
 
 
-@pytest.mark.parametrize("flags", [0, 4])
+@pytest.mark.parametrize("flags", [0, 4, 8])
 def test_both_filter_forms_on_aimed_and_hostile_inputs(torch_cuda, cuda_lib, flags):
-    """The constant-threshold form (default) and the per-molecule-tolerance form (flag 4) separately."""
+    """The constant-threshold form two molecules per thread (default) and one per thread (flag 8), and the
+    per-molecule-tolerance form (flag 4), separately."""
     rng = np.random.default_rng(77 + flags)
     base = standard_ics(64, 9, 3.0)
     hostile = np.repeat(base, 10, axis=1)
