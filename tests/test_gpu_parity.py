@@ -640,7 +640,7 @@ def test_full_size_properties(torch_cuda):
     # (6) work counters: rows + steps account for every trajectory row
     w = b.work.cpu().numpy()
     assert w[3] == int(b.counters[names.index("Inside lens"):].sum())      # lens entries = everything after the entrance
-    assert w[2] == 0 and w[4] == 0
+    assert w[2] == 0 and w[4] <= 1e-5 * w[1]       # no table excursions; a few RK steps per 1e7 redone on the plain path
 
 
 def test_hit_fractions_match_the_reference(torch_cuda, golden_dir):
