@@ -773,7 +773,8 @@ def test_contracted_math_mode(torch_cuda, golden_dir):
         err = np.abs(b["fin"][:, same] - a["fin"][:, same]) / np.maximum(np.abs(a["fin"][:, same]), 1e-9)
         assert err.max() < LOOSE
         assert np.percentile(err, 99.9) < 1e-11                      # what is actually achieved
-        np.testing.assert_array_equal(a["work"][2:5], b["work"][2:5])   # no table excursions, no fallbacks
+        np.testing.assert_array_equal(a["work"][2:4], b["work"][2:4])   # no table excursions, the same lens entries
+        assert b["work"][4] == 0 and a["work"][4] <= 1e-5 * a["work"][1]  # exact mode redoes a few RK steps per 1e7 on the plain path
     # the public API in this mode: saved trajectories are re-propagated with the same arithmetic
     sim = TrajectorySimulator(seed=3, math="contracted")
     sim.run_simulation(bl, "r", N_traj=2_000_000, apertures_of_interest=["Detected", "Inside lens"], n_jobs=10)
