@@ -101,7 +101,9 @@ struct cmt_beamline {
     int n_sm;
     int math;           // CMT_MATH_EXACT / CMT_MATH_CONTRACTED
     double4 *d_tab;     // [tab_total]: (r_j, r_{j+1}, a_j, slope_j)
-    size_t tab_bytes;   // dynamic shared memory the lens/trajectory kernels need
+    size_t tab_bytes;   // dynamic shared memory the tail/trajectory kernels need (every table, plain layout)
+    int seg_copies = 1; // lens_seg_kernel: replication of the first lens' table in shared memory (8, 4, 2 or 1)
+    size_t seg_bytes = 0; // ... and the dynamic shared memory that takes
     bool has_mesh;      // a Honeycomb is present: launch the kernel variants that carry its hit test
     std::vector<struct PlaneD> planes;   // the filter planes in binary64 (thresholds of the quick filter derive from them)
     // staging of the host-buffer entry points: streams, device buffers, workspace.  Owned by the handle, so
@@ -477,17 +479,39 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
             return fail(CMT_ECUDA, "uploading lens tables failed: %s", cudaGetErrorString(e));
         }
         P.tab = bl->d_tab;
-        if (bl->tab_bytes > 40 * 1024) {
+        // lens_seg_kernel keeps only the first lens' table, replicated so that the lanes of a quarter warp read
+        // different bank groups (Table, cmt_device.cuh): the most copies that still leave every CTA the registers
+        // admit (LENS_SEG_MIN_CTAS per SM) its shared memory (227 KB per SM, 1 KB reserved per CTA).  Measured
+        // (profiles/README.md, round 2, 222-point table): 1 / 2 / 4 / 8 copies -> lens stage 0.495 / 0.473 / 0.468 /
+        // 0.472 ms alone at 1e7 molecules, overlapped step 0.365 / 0.350 / 0.345 / 0.352 ms.
+        bl->seg_copies = 1;
+        bl->seg_bytes = 0;
+        if (P.first_lens < P.n_el) {
+            static const int tune_copies = env_int("CMT_TUNE_SEG_COPIES", 0);            // experiments only
+            const size_t one = (size_t)P.el[P.first_lens].tab_len * sizeof(double4);
+            const size_t budget = (size_t)(227 * 1024) / LENS_SEG_MIN_CTAS - 2048;
+            int copies = 8;
+            while (copies > 1 && one * copies > budget) copies >>= 1;
+            if (tune_copies == 1 || tune_copies == 2 || tune_copies == 4 || tune_copies == 8)
+                if (one * tune_copies <= 200 * 1024) copies = tune_copies;
+            bl->seg_copies = copies;
+            bl->seg_bytes = one * copies;
+        }
+        if (bl->tab_bytes > 40 * 1024 || bl->seg_bytes > 40 * 1024) {
             // Tables beyond the default 48 KB of dynamic shared memory need the opt-in.  The attribute is per
             // kernel and per device and must cover EVERY live handle, so it is only ever raised.
             static std::mutex mu;
             static size_t granted[64] = {0};
             std::lock_guard<std::mutex> lk(mu);
-            if (device < 64 && bl->tab_bytes > granted[device]) {
-                const int b = (int)bl->tab_bytes;
+            const size_t need = std::max(bl->tab_bytes, bl->seg_bytes);
+            if (device < 64 && need > granted[device]) {
+                const int b = (int)need;
                 cudaError_t a = cudaSuccess;
                 auto opt_in = [&](const void *fn) { if (a == cudaSuccess) a = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, b); };
-                opt_in((const void *)lens_seg_kernel<false>);   opt_in((const void *)lens_seg_kernel<true>);
+                opt_in((const void *)lens_seg_kernel<false, 1>); opt_in((const void *)lens_seg_kernel<true, 1>);
+                opt_in((const void *)lens_seg_kernel<false, 2>); opt_in((const void *)lens_seg_kernel<true, 2>);
+                opt_in((const void *)lens_seg_kernel<false, 4>); opt_in((const void *)lens_seg_kernel<true, 4>);
+                opt_in((const void *)lens_seg_kernel<false, 8>); opt_in((const void *)lens_seg_kernel<true, 8>);
                 opt_in((const void *)tail_kernel<false, false>); opt_in((const void *)tail_kernel<false, true>);
                 opt_in((const void *)tail_kernel<true, false>);  opt_in((const void *)tail_kernel<true, true>);
                 opt_in((const void *)trajectory_kernel<false>); opt_in((const void *)trajectory_kernel<true>);
@@ -497,7 +521,7 @@ extern "C" int cmt_beamline_create(const cmt_element_t *elements, int n_elements
                     delete bl;
                     return fail(CMT_ECUDA, "shared-memory opt-in for %d B of lens tables failed: %s", b, cudaGetErrorString(a));
                 }
-                granted[device] = bl->tab_bytes;
+                granted[device] = need;
             }
         }
     }
@@ -727,7 +751,7 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.blockDim = dim3(LENS_THREADS);
-        cfg.dynamicSmemBytes = bl->tab_bytes; cfg.stream = st; cfg.attrs = &attr; cfg.numAttrs = 1;
+        cfg.dynamicSmemBytes = bl->seg_bytes; cfg.stream = st; cfg.attrs = &attr; cfg.numAttrs = 1;
 
         const int n_steps = bl->P.el[bl->P.first_lens].n_steps;
         constexpr int max_seg = (int)(WS_HEADER / 16) - 2;                          // a (count, cursor) pair per segment
@@ -738,6 +762,11 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
         const int64_t max_ctas = (n + LENS_THREADS - 1) / LENS_THREADS;
         cfg.gridDim = dim3((unsigned)std::min<int64_t>(max_ctas, (int64_t)bl->n_sm * seg_per_sm));
         X.q = Q.q + (size_t)(n_seg & 1) * QUEUE_COMPONENTS * (size_t)Q.cap;   // the last segment's unused output array
+        using SegFn = void (*)(const Params, int64_t, const cmt_outputs_t, Queue, Queue, Queue, int);
+        static const SegFn seg_fn[2][4] = {
+            {lens_seg_kernel<false, 1>, lens_seg_kernel<false, 2>, lens_seg_kernel<false, 4>, lens_seg_kernel<false, 8>},
+            {lens_seg_kernel<true, 1>, lens_seg_kernel<true, 2>, lens_seg_kernel<true, 4>, lens_seg_kernel<true, 8>}};
+        const int copies_log2 = bl->seg_copies == 8 ? 3 : bl->seg_copies == 4 ? 2 : bl->seg_copies == 2 ? 1 : 0;
         for (int k = 0; k < n_seg; ++k) {
             Queue A, B;
             A.cap = B.cap = Q.cap;
@@ -747,8 +776,7 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
             A.cursor = A.count + 1;
             B.count = Q.count + 4 + 2 * k;
             B.cursor = B.count + 1;
-            if (contract) CUDA_TRY(cudaLaunchKernelEx(&cfg, lens_seg_kernel<true>, bl->P, first_index, *out, A, B, X, seg));
-            else CUDA_TRY(cudaLaunchKernelEx(&cfg, lens_seg_kernel<false>, bl->P, first_index, *out, A, B, X, seg));
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, seg_fn[contract][copies_log2], bl->P, first_index, *out, A, B, X, seg));
             count_launch();
         }
         const int grid_tail = (int)std::min<int64_t>((n + TRAJ_THREADS - 1) / TRAJ_THREADS, (int64_t)bl->n_sm * 8);

@@ -377,7 +377,9 @@ constexpr int LENS_SEG_GRID_CTAS = 3;     // CTAs per SM one launch asks for: le
                                           // lens stage 0.481 / 0.514 / 0.535 ms at 1e7 molecules, 2.55 / 2.81 / 2.94 ms at 8e7
 #endif
 
-template <bool CONTRACT>
+// COPIES: how many times the first lens' table is replicated in shared memory (Table, cmt_device.cuh); the host
+// picks the largest of 8, 4, 2, 1 that leaves room for LENS_SEG_MIN_CTAS CTAs per SM (cmt_api.cu: seg_copies).
+template <bool CONTRACT, int COPIES>
 __global__ void __launch_bounds__(LENS_THREADS, LENS_SEG_MIN_CTAS)
 lens_seg_kernel(const __grid_constant__ Params P, int64_t first_index, const __grid_constant__ cmt_outputs_t O,
                 Queue A, Queue B, Queue X, int seg_steps)
@@ -388,14 +390,14 @@ lens_seg_kernel(const __grid_constant__ Params P, int64_t first_index, const __g
     const unsigned long long n_groups = (count + 31ull) / 32ull;      // one group = one full warp
     // when the queue cannot occupy every warp, only the first ceil(n_groups / warps per CTA) CTAs take part
     if ((unsigned long long)blockIdx.x * (LENS_THREADS / 32) >= n_groups) return;
-    for (int i = threadIdx.x; i < P.tab_total; i += blockDim.x) smem_tab[i] = P.tab[i];
-    block_acc_init(acc);
     const DevElement &E = P.el[P.first_lens];
+    fill_replicated<COPIES>(reinterpret_cast<double2 *>(smem_tab), P.tab, E);
+    block_acc_init(acc);
     const int n_steps = E.n_steps;
     const double bore_T = E.p[0];
-    const Table tb = table_of(E, smem_tab);
+    const Table tb = table_replicated<COPIES>(E, reinterpret_cast<const double2 *>(smem_tab));
     const bool reference_math = (P.flags & CMT_FLAG_REFERENCE_MATH) != 0 || !tb.fast;
-    const double r_last = tb.t[tb.n - 1].x;
+    const double r_last = tb.rw(tb.n - 1).x;
     unsigned rows_total = 0, steps_total = 0, oob_total = 0, ref_total = 0;
 
     for (;;) {
@@ -431,8 +433,8 @@ lens_seg_kernel(const __grid_constant__ Params P, int64_t first_index, const __g
 #pragma unroll LENS_UNROLL
             while (step < end_step) {
                 int oob = 0;
-                if (CONTRACT) lens_step_contracted(tb, r_last, lc, m, P.g, oob);
-                else lens_step(tb, lc, m, s_xy, P.g, oob, reference_math);
+                if (CONTRACT) lens_step_contracted<COPIES>(tb, r_last, lc, m, P.g, oob);
+                else lens_step<COPIES>(tb, lc, m, s_xy, P.g, oob, reference_math);
                 oob_total += oob & 0xffff;
                 ref_total += oob >> 16;
                 ++steps_total;

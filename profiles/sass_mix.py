@@ -16,7 +16,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 CSRC = ROOT / "centrex-molecule-trajectories_b200" / "csrc"
 STUB = """#include "cmt_kernels.cuh"
-void *cmt_stub_keep() { return (void *)cmt::lens_seg_kernel<%s>; }
+void *cmt_stub_keep() { return (void *)cmt::lens_seg_kernel<%s, %s>; }
 """
 
 
@@ -25,7 +25,8 @@ def main():
     contract = "true" if "--contracted" in sys.argv else "false"
     with tempfile.TemporaryDirectory() as td:
         src, cubin = Path(td) / "stub.cu", Path(td) / "stub.cubin"
-        src.write_text(STUB % contract)
+        copies = next((a.split("=")[1] for a in sys.argv[1:] if a.startswith("--copies=")), "8")
+        src.write_text(STUB % (contract, copies))
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-cubin", "-I", str(CSRC),
                "-I", str(ROOT / "include"), "-Xptxas", "-v", *flags, "-o", str(cubin), str(src)]
         out = subprocess.run(cmd, capture_output=True, text=True)
