@@ -851,10 +851,39 @@ extern "C" int cmt_trajectories(const cmt_beamline_t *bl, int64_t n, const doubl
         ScopedTimer tm(2, st);
         if (bl->math == CMT_MATH_CONTRACTED)
             trajectory_kernel<true><<<grid, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, n, state, n_comp, state_ld, select,
-                                                                               select_base, rows, max_rows, row_offset, n_rows, fate);
+                                                                               select_base, rows, max_rows, row_offset, n_rows, fate,
+                                                                               nullptr, 0);
         else
             trajectory_kernel<false><<<grid, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, n, state, n_comp, state_ld, select,
-                                                                                select_base, rows, max_rows, row_offset, n_rows, fate);
+                                                                                select_base, rows, max_rows, row_offset, n_rows, fate,
+                                                                                nullptr, 0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return CMT_OK;
+}
+
+extern "C" int cmt_resume(const cmt_beamline_t *bl, int64_t n, const double *state, int64_t state_ld,
+                          double *last_row, int64_t last_ld, int32_t *n_rows, uint8_t *fate, void *stream)
+{
+    if (!bl) return fail(CMT_EINVAL, "beamline handle is NULL");
+    if (n < 0) return fail(CMT_EINVAL, "n < 0");
+    if (n == 0) return CMT_OK;
+    if (!state) return fail(CMT_EINVAL, "state is NULL");
+    if (!last_row && !n_rows && !fate) return fail(CMT_EINVAL, "nothing to compute: last_row, n_rows and fate are all NULL");
+    if (state_ld < n || (last_row && last_ld < n)) return fail(CMT_EINVAL, "leading dimension smaller than n");
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceGuard guard(bl->device);
+    CUDA_TRY(guard.status);
+    const int grid = (int)((n + TRAJ_THREADS - 1) / TRAJ_THREADS);
+    {
+        ScopedTimer tm(2, st);
+        if (bl->math == CMT_MATH_CONTRACTED)
+            trajectory_kernel<true><<<grid, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, n, state, 10, state_ld, nullptr, 0, nullptr, 1,
+                                                                               nullptr, n_rows, fate, last_row, last_ld);
+        else
+            trajectory_kernel<false><<<grid, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, n, state, 10, state_ld, nullptr, 0, nullptr, 1,
+                                                                                nullptr, n_rows, fate, last_row, last_ld);
+        count_launch();
     }
     CUDA_TRY(cudaGetLastError());
     return CMT_OK;

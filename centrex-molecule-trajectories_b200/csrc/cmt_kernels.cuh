@@ -541,7 +541,8 @@ __global__ void __launch_bounds__(TRAJ_THREADS)
 trajectory_kernel(const __grid_constant__ Params P, int64_t n, const double *__restrict__ state, int n_comp,
                   int64_t state_ld, const int64_t *__restrict__ select, int64_t select_base,
                   double *__restrict__ rows, int max_rows, const int64_t *__restrict__ row_offset,
-                  int32_t *__restrict__ n_rows, uint8_t *__restrict__ fate_out)
+                  int32_t *__restrict__ n_rows, uint8_t *__restrict__ fate_out,
+                  double *__restrict__ last_row, int64_t last_ld)
 {
     extern __shared__ double4 smem_tab[];
     for (int i = threadIdx.x; i < P.tab_total; i += blockDim.x) smem_tab[i] = P.tab[i];
@@ -575,6 +576,14 @@ trajectory_kernel(const __grid_constant__ Params P, int64_t n, const double *__r
     if (fate < 0) fate = P.fate_detected;
     if (n_rows) n_rows[j] = rec.n;
     if (fate_out) fate_out[j] = (uint8_t)fate;
+    if (last_row) {
+        // the molecule's last committed row (cmt_resume): where it was stopped, or where the last element left it
+        double *r = last_row + j;
+        r[0 * last_ld] = m.x;  r[1 * last_ld] = m.y;  r[2 * last_ld] = m.z;
+        r[3 * last_ld] = m.vx; r[4 * last_ld] = m.vy; r[5 * last_ld] = m.vz;
+        r[6 * last_ld] = m.ax; r[7 * last_ld] = m.ay; r[8 * last_ld] = 0.0;
+        r[9 * last_ld] = m.t;
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -13,11 +13,10 @@ import numpy as np
 from . import _engine as eng
 
 
-def propagate_molecule(elements, molecule, mark_detected: bool) -> None:
+def _device_run(elements, molecule) -> None:
+    """Built-in elements: the molecule's last row goes to the trajectory kernel, every new row comes back."""
     torch = eng._torch()
-    if not getattr(molecule, "alive", True):
-        return
-    prop = eng.Propagator(eng.flatten(sorted(elements, key=lambda e: e.z0)))
+    prop = eng.Propagator(eng.flatten(elements))
     tr = molecule.trajectory
     last = tr.n - 1
     state = np.empty((10, 1), dtype=np.float64)
@@ -27,11 +26,32 @@ def propagate_molecule(elements, molecule, mark_detected: bool) -> None:
     rows, offsets, fate = prop.trajectories(torch.from_numpy(state).to(prop.tdev))
     tr.extend_rows(rows[1:int(offsets[1])])   # row 0 repeats the molecule's current row
     name = prop.flat.fate_names[int(fate[0])]
-    if name == "Detected":
-        if mark_detected:
-            molecule.set_aperture_hit("Detected")
-    else:
+    if name != "Detected":
         molecule.set_dead()
         molecule.set_aperture_hit(name)
+
+
+def propagate_molecule(elements, molecule, mark_detected: bool) -> None:
+    from ._hybrid import runs_on_device
+
+    if not getattr(molecule, "alive", True):
+        return
+    run = []
+    for element in sorted(elements, key=lambda e: e.z0):
+        if runs_on_device(element):
+            run.append(element)
+            continue
+        if run:
+            _device_run(run, molecule)
+            run = []
+        if not molecule.alive:
+            break
+        element.propagate_through(molecule)          # a user-defined element: its own Python code (beamline.py:26-31)
+        if not molecule.alive:
+            break
+    if run and molecule.alive:
+        _device_run(run, molecule)
     if mark_detected:
-        tr.drop_nans()
+        if molecule.alive:
+            molecule.set_aperture_hit("Detected")
+        molecule.trajectory.drop_nans()

@@ -28,6 +28,7 @@ from typing import List, Optional
 import numpy as np
 
 from . import _engine as eng
+from . import _hybrid
 from .beamline import Beamline
 from .distributions import CeNTREXPositionDistribution, CeNTREXVelocityDistribution, Distribution
 from .molecule import Molecule
@@ -201,6 +202,10 @@ class TrajectorySimulator:
         N = int(N_traj / N_loops)
         total = N * N_loops
 
+        if _hybrid.is_hybrid(beamline.elements):
+            # user-defined elements: the built-in runs on the GPU, the user's propagate_through on the host (_hybrid.py)
+            return self._run_hybrid(beamline, run_name, vdist, xdist, N, N_loops, total, apertures_of_interest, seed)
+
         flat = eng.flatten(beamline.elements)
         prop = eng.Propagator(flat, self.device, math=self.math)
         prop.reset()
@@ -210,15 +215,7 @@ class TrajectorySimulator:
         molecules: List[Molecule] = []
 
         if source is not None:
-            if seed is None:
-                seed = self.seed
-            if seed is None:
-                # honours np.random.seed(): the reference draws from NumPy's global RNG
-                seed = int(np.random.randint(0, 2**62))
-                if world > 1:
-                    s = torch.tensor([seed], dtype=torch.int64, device=prop.tdev if torch.distributed.get_backend() == "nccl" else "cpu")
-                    torch.distributed.broadcast(s, 0)
-                    seed = int(s.item())
+            seed = self._pick_seed(seed, prop.tdev)
             lo, hi = eng.shard_range(total, rank, world)
             chunk = prop.fit_chunk(self.chunk)
             if not save_mask and (1 << 21) <= hi - lo <= chunk:
@@ -285,6 +282,50 @@ class TrajectorySimulator:
         offset, n_saved = sum(saved_counts[:rank]), sum(saved_counts)
         self.result = SimulationResult(self.counter, beamline, xdist, vdist, molecules, offset, n_saved)
         self.results[run_name] = SimulationResult(self.counter, beamline, xdist, vdist, molecules, offset, n_saved)
+
+    def _pick_seed(self, seed, tdev) -> int:
+        """Seed of the device source: the call's, the simulator's, or one drawn from NumPy's global RNG (which honours
+        np.random.seed() as the reference's draws do) and agreed on by all ranks."""
+        torch = eng._torch()
+        if seed is None:
+            seed = self.seed
+        if seed is None:
+            seed = int(np.random.randint(0, 2**62))
+            _rank, world = eng.dist_info()
+            if world > 1:
+                s = torch.tensor([seed], dtype=torch.int64, device=tdev if torch.distributed.get_backend() == "nccl" else "cpu")
+                torch.distributed.broadcast(s, 0)
+                seed = int(s.item())
+        return int(seed)
+
+    def _run_hybrid(self, beamline, run_name, vdist, xdist, N, N_loops, total, apertures_of_interest, seed) -> None:
+        """run_simulation for a beamline with user-defined elements: same sample, same sharding, same result objects;
+        the Counter is keyed by whatever fate names the user's elements report."""
+        torch = eng._torch()
+        run = _hybrid.HybridRun(beamline.elements, self.device, self.math, list(apertures_of_interest))
+        rank, world = eng.dist_info()
+        source = eng.make_source(vdist, xdist)
+        if source is not None:
+            seed = self._pick_seed(seed, run.tdev)
+            lo, hi = eng.shard_range(total, rank, world)
+            step = min(self.chunk, _hybrid.HYBRID_CHUNK)
+            for first in range(lo, hi, step):
+                run.run_chunk(_hybrid.draw_ic(source, seed, first, min(step, hi - first), run.device))
+        else:
+            for vs, xs in eng.owned_draws(vdist, xdist, N, N_loops, rank, world):
+                host = np.ascontiguousarray(np.concatenate([xs, vs], axis=0), dtype=np.float64)
+                run.run_chunk(torch.from_numpy(host).to(run.tdev))
+        self.last_work = run.work
+        if run.work[2] > 0:
+            raise ValueError(f"A value in x_new is above the interpolation range ({int(run.work[2])} lens force "
+                             "evaluations fell outside the a_interp table)")
+        self.counter = Counter()
+        for name, c in _hybrid.merge_counts_across_ranks(run.counts).items():
+            self.counter.increment_counter(name, int(c))
+        saved_counts = eng.gather_counts(len(run.molecules), run.device)
+        offset, n_saved = sum(saved_counts[:rank]), sum(saved_counts)
+        self.result = SimulationResult(self.counter, beamline, xdist, vdist, run.molecules, offset, n_saved)
+        self.results[run_name] = SimulationResult(self.counter, beamline, xdist, vdist, run.molecules, offset, n_saved)
 
     # the reference's README calls the parallel entry point by this name (README.md:52)
     run_simulation_parallel = run_simulation

@@ -190,6 +190,17 @@ int cmt_trajectories(const cmt_beamline_t *bl, int64_t n, const double *state, i
                      double *rows, int32_t max_rows, const int64_t *row_offset, int32_t *n_rows,
                      uint8_t *fate, void *stream);
 
+/* Bulk form of BeamlineElement.propagate_through(molecule) for molecules that are already in flight
+ * (apertures.py:38-42 called on a live Molecule; beamline.py:26-31 for the elements of this handle): molecule j
+ * resumes from the row state[0..9][j] = x,y,z,vx,vy,vz,ax,ay,az,t (device, SoA [10][state_ld]; a_z must be 0) and
+ * is walked through every element of the handle.  Outputs (device, each optional): last_row [10][last_ld] = the
+ * last row of its trajectory (where it was stopped, or where the last element left it), n_rows[j] = rows it
+ * would have recorded including the row it resumed from, fate[j] (the handle's "Detected" id = still alive).
+ * This is the hand-back step for beamlines with elements implemented outside this library: the caller runs its
+ * own element on the survivors of one handle and resumes them on the handle of the elements behind it. */
+int cmt_resume(const cmt_beamline_t *bl, int64_t n, const double *state, int64_t state_ld,
+               double *last_row, int64_t last_ld, int32_t *n_rows, uint8_t *fate, void *stream);
+
 /* State of n selected molecules where they cross given z planes, without
  * storing trajectories: the device form of find_radial_pos_dist / find_vel_dist
  * (post_processing.py:20-140) — last row before the plane flown ballistically
