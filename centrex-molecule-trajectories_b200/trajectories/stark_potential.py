@@ -4,15 +4,22 @@ Mirror of the reference's `stark_potential(state, Ezs)` (stark_potential.py:9-67
 Ezs in V/cm, result in joule.  The reference needs the external, unpinned
 `centrex_TlF` package; when it is importable the full Hamiltonian is used
 exactly as there (minus the blocking plt.show() of lines 63-65), otherwise the
-build's rigid-rotor model (`_tlf.py`) supplies the curve -- parity at this
-boundary is unpinned either way, and the table it feeds
-(`ElectrostaticLens.a_interp`) can always be injected by the caller.
+build's own X-state Hamiltonian (`_tlf_full.py`: rotation, Stark, hyperfine and
+Zeeman terms in the same 196-state uncoupled basis, the state followed by the
+same overlap re-ordering) supplies the curve.  Parity at this boundary is
+unpinned either way (nothing in the reference pins centrex_TlF's numbers), and
+the table the curve feeds (`ElectrostaticLens.a_interp`) can always be injected
+by the caller.  `MODEL = "rigid"` selects the bare rigid rotor of `_tlf.py`
+(no hyperfine structure; within 1e-5 of the full curve at lens fields).
 """
 from __future__ import annotations
 
 import numpy as np
 
-from . import _tlf
+from . import _tlf, _tlf_full
+
+_CURVES: dict = {}
+MODEL = "full"      # "full": _tlf_full (the reference's physics); "rigid": _tlf.rigid_rotor_stark_joule
 
 try:  # pragma: no cover - not installed in the build image
     from centrex_TlF.hamiltonian import generate_uncoupled_hamiltonian_X  # type: ignore  # noqa: F401
@@ -33,9 +40,18 @@ def default_lens_state():
                                    electronic_state="X")
 
 
+def state_spin_projections(state):
+    """(m1, m2) of the state's largest component; the nuclear spins of electrostatic_lens.py:33-43 for a bare
+    (J, mJ) pair."""
+    if isinstance(state, (tuple, list)):
+        return (float(state[2]), float(state[3])) if len(state) >= 4 else (0.5, -0.5)
+    c = state.find_largest_component()
+    return float(c.m1), float(c.m2)
+
+
 def state_quantum_numbers(state):
     """(J, mJ) of the state's largest component (electrostatic_lens.py:176-177)."""
-    if isinstance(state, (tuple, list)) and len(state) == 2:
+    if isinstance(state, (tuple, list)) and len(state) in (2, 4):
         return int(state[0]), int(state[1])
     c = state.find_largest_component()
     return int(c.J), int(c.mJ)
@@ -76,4 +92,14 @@ def stark_potential(state, Ezs):
     if HAVE_CENTREX_TLF:  # pragma: no cover
         return _stark_centrex_tlf(state, Ezs)
     J, mJ = state_quantum_numbers(state)
-    return _tlf.rigid_rotor_stark_joule(J, mJ, Ezs)
+    if MODEL == "rigid":
+        return _tlf.rigid_rotor_stark_joule(J, mJ, Ezs)
+    m1, m2 = state_spin_projections(state)
+    # a sweep or a loop of runs asks for the same curve again and again (25 ms each: 222 small eigh calls)
+    key = (J, mJ, m1, m2, Ezs.shape, Ezs.tobytes())
+    hit = _CURVES.get(key)
+    if hit is None:
+        if len(_CURVES) >= 256:
+            _CURVES.clear()
+        hit = _CURVES[key] = _tlf_full.stark_joule(J, mJ, m1, m2, Ezs)
+    return hit.copy()

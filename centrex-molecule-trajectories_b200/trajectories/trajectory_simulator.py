@@ -378,12 +378,28 @@ class TrajectorySimulator:
         if seed is None:
             seed = int(eng.broadcast_object(int(np.random.randint(0, 2**62))))
 
-        # one flattening per point, differing only in the lens table
+        # the Stark tables of all points, built side by side (each is a chain of small LAPACK calls that release
+        # the GIL), then one flattening per point, differing only in the lens table
+        def table_of(point):
+            probe = shallow(lens)
+            probe.state, probe.V, probe.a_interp = point[0], point[1], None
+            return probe.ensure_a_interp()
+
+        from concurrent.futures import ThreadPoolExecutor
+        from contextlib import nullcontext
+
+        try:        # the matrices are 26 x 26 at most: BLAS threads of their own only get in each other's way
+            from threadpoolctl import threadpool_limits
+            one_blas_thread = threadpool_limits(1)
+        except Exception:
+            one_blas_thread = nullcontext()
+        with one_blas_thread, ThreadPoolExecutor(max_workers=max(1, min(len(points), os.cpu_count() or 1, 8))) as pool:
+            interps = list(pool.map(table_of, points))
         flats, keys, lenses = [], [], []
         saved_state, saved_V, saved_tab = lens.state, lens.V, lens.a_interp
         try:
-            for state, V in points:
-                lens.state, lens.V, lens.a_interp = state, V, None
+            for (state, V), interp in zip(points, interps):
+                lens.state, lens.V, lens.a_interp = state, V, interp
                 flats.append(eng.flatten(beamline.elements))
                 J, mJ = state_quantum_numbers(state)
                 keys.append((J, mJ, V))

@@ -147,7 +147,7 @@ def test_plane_crossings_host(golden_dir):
     assert seen_rows > 5000
 
 
-def test_table_builder_matches_reference_builder(golden_dir):
+def test_table_builder_matches_reference_builder(golden_dir, monkeypatch):
     """L4: `_tlf.lens_acceleration_table` (what ElectrostaticLens.ensure_a_interp calls) against the table the
     reference's OWN builder produced (electrostatic_lens.py:194-209 executed by tests/golden/make_golden.py with only
     `stark_potential` substituted): grid length and extent, the nominal-dr gradient, the division by the mass and
@@ -156,6 +156,10 @@ def test_table_builder_matches_reference_builder(golden_dir):
     from trajectories.beamline_elements.electrostatic_lens import ElectrostaticLens
     from trajectories.stark_potential import UncoupledBasisState
 
+    from trajectories import stark_potential as sp
+
+    # the fixture was generated with the rigid-rotor curve substituted for centrex_TlF's: the builder is what is pinned
+    monkeypatch.setattr(sp, "MODEL", "rigid")
     g = np.load(golden_dir / "table_builder.npz")
     mass = (204.38 + 19.00) * 1.67e-27
     assert len(g["points"]) >= 3
