@@ -643,6 +643,9 @@ static int check_outputs(const cmt_beamline_t *bl, const cmt_outputs_t *out, int
     if (out->final_state && out->final_ld < n) return fail(CMT_EINVAL, "outputs.final_ld < n");
     if (out->saved_index && (!out->saved_count || out->saved_capacity < 0))
         return fail(CMT_EINVAL, "outputs.saved_index needs saved_count and a capacity");
+    if (out->queue_capacity < 0) return fail(CMT_EINVAL, "outputs.queue_capacity < 0");
+    if (out->queue_capacity > 0 && !out->work)
+        return fail(CMT_EINVAL, "outputs.queue_capacity needs outputs.work (work[6] reports dropped molecules)");
     return CMT_OK;
 }
 
@@ -656,10 +659,11 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
     if (n == 0) return CMT_OK;
     if (n >= (1ll << SEG_INDEX_BITS)) return fail(CMT_EINVAL, "n must be below 2^%d per launch", SEG_INDEX_BITS);
     const bool has_lens = bl->P.first_lens < bl->P.n_el;
-    const size_t need = cmt_workspace_bytes(bl, n);
+    const int64_t q_cap = out->queue_capacity > 0 ? std::min<int64_t>(out->queue_capacity, n) : n;
+    const size_t need = cmt_workspace_bytes(bl, q_cap);
     if (!workspace || workspace_bytes < need)
-        return fail(CMT_ENOMEM, "workspace of %zu B given, %zu B needed for n=%lld", workspace_bytes, need,
-                    (long long)n);
+        return fail(CMT_ENOMEM, "workspace of %zu B given, %zu B needed for n=%lld with a lens queue of %lld", workspace_bytes,
+                    need, (long long)n, (long long)q_cap);
     if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return fail(CMT_EINVAL, "workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     DeviceGuard guard(bl->device);
@@ -669,7 +673,7 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
     Q.count = reinterpret_cast<unsigned long long *>(workspace);
     Q.cursor = Q.count + 1;
     Q.q = reinterpret_cast<double *>(static_cast<char *>(workspace) + WS_HEADER);
-    Q.cap = has_lens ? n : 0;
+    Q.cap = has_lens ? q_cap : 0;
     // header words: [0],[1] entry queue (count, cursor); [2],[3] exit queue; [4+2k],[5+2k] output of lens segment k
     Queue X;
     X.count = Q.count + 2;

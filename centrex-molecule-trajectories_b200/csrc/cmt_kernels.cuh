@@ -172,6 +172,10 @@ __device__ __forceinline__ void walk_exact(const Params &P, const cmt_source_t &
         q[3 * Q.cap] = m.vx; q[4 * Q.cap] = m.vy; q[5 * Q.cap] = m.vz;
         q[6 * Q.cap] = m.t;
         q[7 * Q.cap] = __longlong_as_double(i);
+    } else if (to_lens) {
+        // a queue smaller than the launch (cmt_outputs_t.queue_capacity) is full: the molecule is dropped and
+        // counted, and the caller repeats the launch with a larger queue
+        atomicAdd(&acc.work[6], 1ull);
     }
     retire(valid && !to_lens, fate, m, i, first_index + i, acc, O);
 }

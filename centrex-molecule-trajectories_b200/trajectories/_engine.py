@@ -16,9 +16,11 @@ import numpy as np
 from . import _native as nat
 
 G = 9.80665  # scipy.constants.g (molecule.py:6)
-DEFAULT_CHUNK = 1 << 26          # molecules per launch: 8.6 GB of lens-queue workspace per stream slot (2 x 64 B per molecule); larger
-                                 # launches keep the lens integrator's lanes refilled (1e10 molecules: 0.81 s at
-                                 # 2^24, 0.73 s at 2^26)
+DEFAULT_CHUNK = 1 << 26          # molecules per launch: larger launches keep the lens integrator's lanes refilled (1e10
+                                 # molecules: 0.81 s at 2^24, 0.73 s at 2^26).  The lens-queue workspace of a launch is
+                                 # 2 x 64 B per queue entry: 8.6 GB per stream slot if the queue is sized for every
+                                 # molecule, 0.13 GB when it is sized from a pilot launch (Propagator.queue_capacity)
+PILOT_MOLECULES = 1 << 21        # first launch of a large Philox run: full-size queue, its lens-entry count sizes the rest
 ROW_BUDGET_BYTES = 1 << 30       # device bytes per saved-trajectory batch
 PINNED_RESULT_BYTES = 2 << 30    # saved-trajectory blocks up to this size are returned in page-locked memory
 
@@ -262,6 +264,27 @@ class Propagator:
         self._ws = [None] * (self.n_slots + 1)           # last entry: launches on the current stream
         self._saved_count = [torch.zeros(1, dtype=torch.int64, device=self.tdev) for _ in range(self.n_slots + 1)]
         self._streams = None
+        self.entry_fraction = None                       # lens entries per molecule seen by a pilot launch (None: unknown)
+
+    # -- lens-queue sizing -------------------------------------------------------
+    def queue_capacity(self, n: int) -> int:
+        """Lens-queue entries for a launch of n molecules: all n while nothing is known about the source; after
+        `learn_entry_fraction()` the expected number of molecules that reach the lens plus 25 % and six standard
+        deviations, at least n / 64.  A launch that overflows its queue drops molecules and says so in work[6];
+        `queue_overflow()` reads it."""
+        if self.entry_fraction is None:
+            return int(n)
+        mean = self.entry_fraction * n
+        return int(min(n, max(n // 64, 1.25 * mean + 6.0 * mean ** 0.5 + 4096)))
+
+    def learn_entry_fraction(self, n_launched: int) -> float:
+        """Read the work counters (one synchronisation) after `n_launched` molecules and size later queues from them."""
+        w = self.work.cpu().numpy()
+        self.entry_fraction = float(w[3]) / max(int(n_launched), 1)
+        return self.entry_fraction
+
+    def queue_overflow(self) -> int:
+        return int(self.work[6].item())
 
     def reset(self):
         self.join()
@@ -281,7 +304,7 @@ class Propagator:
         self.work = torch.zeros(8, dtype=torch.int64, device=self.tdev)
 
     def release(self):
-        """Give the queue workspaces back to the allocator (8.6 GB per stream slot at the default chunk)."""
+        """Give the queue workspaces back to the allocator."""
         self.join()
         _torch().cuda.current_stream(self.device).synchronize()
         self._ws = [None] * (self.n_slots + 1)
@@ -291,7 +314,8 @@ class Propagator:
         the saved-index buffer) fit into `fraction` of the device memory that is free right now."""
         free, _total = _torch().cuda.mem_get_info(self.device)
         held = sum(w.numel() for w in self._ws if w is not None)
-        per_molecule = (self.n_slots + 1) * 2 * 8 * 8 + 16
+        queue_share = self.queue_capacity(1 << 26) / float(1 << 26)
+        per_molecule = (self.n_slots + 1) * 2 * 8 * 8 * queue_share + 16
         fit = int(fraction * (free + held)) // per_molecule
         return max(1 << 20, min(int(chunk), fit))
 
@@ -345,7 +369,7 @@ class Propagator:
 
     def _workspace(self, n: int, index: int):
         torch = _torch()
-        need = self.dev.workspace_bytes(n)
+        need = self.dev.workspace_bytes(self.queue_capacity(n))
         if self._ws[index] is None or self._ws[index].numel() < need:
             self._ws[index] = torch.empty(need, dtype=torch.uint8, device=self.tdev)
         return self._ws[index]
@@ -362,6 +386,8 @@ class Propagator:
             O.final_state, O.final_ld = final.data_ptr(), n
         O.counters = self.counters.data_ptr()
         O.work = self.work.data_ptr()
+        cap = self.queue_capacity(n)
+        O.queue_capacity = cap if cap < n else 0
         if save_mask:
             self._saved_count[index].zero_()
             O.saved_index = saved_buf.data_ptr()

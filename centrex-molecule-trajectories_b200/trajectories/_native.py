@@ -55,6 +55,7 @@ class Outputs(C.Structure):
         ("counters", C.c_void_p), ("work", C.c_void_p),
         ("saved_index", C.c_void_p), ("saved_count", C.c_void_p),
         ("saved_capacity", C.c_int64), ("save_mask", C.c_uint64),
+        ("queue_capacity", C.c_int64),
     ]
 
 

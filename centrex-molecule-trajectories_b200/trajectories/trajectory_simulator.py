@@ -217,6 +217,18 @@ class TrajectorySimulator:
         if source is not None:
             seed = self._pick_seed(seed, prop.tdev)
             lo, hi = eng.shard_range(total, rank, world)
+            lo0 = lo
+            if hi - lo > 8 * eng.PILOT_MOLECULES:
+                # A large run starts with a pilot launch whose lens queue could hold every molecule; the fraction that
+                # actually reaches the lens (0.54 % for the CeNTREX source) then sizes the queues of all later launches:
+                # 128 B x n per stream slot would be 8.6 GB at the default chunk, to hold a queue that is 0.5 % full.
+                # The result does not depend on where a run is cut.  A queue that overflows all the same (work[6]) sends
+                # the whole run through full-size queues below.
+                res = prop.propagate_philox(source, seed, lo, eng.PILOT_MOLECULES, save_mask=save_mask)
+                if save_mask and res.saved_index.numel():
+                    molecules.extend(self._collect(prop, prop.draw(source, seed, index=res.saved_index)))
+                prop.learn_entry_fraction(eng.PILOT_MOLECULES)
+                lo += eng.PILOT_MOLECULES
             chunk = prop.fit_chunk(self.chunk)
             if not save_mask and (1 << 21) <= hi - lo <= chunk:
                 # a run that fits one chunk goes out as two halves on two streams: the walk kernel of the
@@ -233,6 +245,18 @@ class TrajectorySimulator:
                     ic = prop.draw(source, seed, index=res.saved_index)
                     molecules.extend(self._collect(prop, ic))
             prop.join()
+            if prop.entry_fraction is not None and prop.queue_overflow():
+                # the sized queues were too small after all: once more, with queues that hold everything
+                prop.reset()
+                prop.entry_fraction = None
+                molecules = []
+                chunk = prop.fit_chunk(self.chunk)
+                for k, first in enumerate(range(lo0, hi, chunk)):
+                    n = min(chunk, hi - first)
+                    res = prop.propagate_philox(source, seed, first, n, save_mask=save_mask, slot=None if save_mask else k)
+                    if save_mask and res.saved_index.numel():
+                        molecules.extend(self._collect(prop, prop.draw(source, seed, index=res.saved_index)))
+                prop.join()
         else:
             # Host draws, replayed.  The reference's N_loops chunks are split into one contiguous block of loops per
             # rank.  A Distribution object is opaque (it may draw from NumPy's global RNG, which scripts seed the same

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CMT_VERSION 100          /* 0.1.0 */
+#define CMT_VERSION 101          /* 0.1.1: cmt_outputs_t.queue_capacity, cmt_resume */
 #define CMT_MAX_ELEMENTS 40      /* element table lives in kernel-parameter constant memory */
 #define CMT_MAX_FATES 64         /* fates are stored as uint8 and selected by a 64-bit mask */
 #define CMT_MAX_TABLES 8
@@ -120,11 +120,17 @@ typedef struct cmt_outputs {
     int64_t *counters;      /* [n_fates] per-fate counts, ACCUMULATED (Counter, trajectory_simulator.py:106-124); required */
     int64_t *work;          /* [CMT_WORK_SLOTS] accumulated: ballistic rows, lens RK steps, table out-of-range
                              * evaluations, lens entries, RK steps that took the plain-intrinsic path, molecules whose
-                             * fate the FP32 filter of the walk kernel decided, 2 reserved; or NULL */
+                             * fate the FP32 filter of the walk kernel decided, molecules dropped by a full lens
+                             * queue (see queue_capacity), 1 reserved; or NULL */
     int64_t *saved_index;   /* [saved_capacity] global indices of molecules whose fate is in save_mask (unordered), or NULL */
     int64_t *saved_count;   /* [1] accumulated cursor into saved_index (may exceed capacity: then the list is truncated) */
     int64_t saved_capacity;
     uint64_t save_mask;     /* bit f set: fate f is an "aperture of interest" (trajectory_simulator.py:75-76) */
+    int64_t queue_capacity; /* 0 (default): the lens queue holds all n molecules of the launch.  k > 0: it holds k
+                             * (workspace of cmt_workspace_bytes(bl, k) bytes); only ~0.5 % of a CeNTREX sample
+                             * reaches the lens.  Molecules that find the queue full are DROPPED -- no fate, no
+                             * Counter entry -- and counted in work[6]: a caller that sets this must pass `work`,
+                             * read work[6] and repeat the launch with a larger capacity when it is not zero. */
 } cmt_outputs_t;
 
 typedef struct cmt_beamline cmt_beamline_t;

@@ -22,8 +22,8 @@ def test_library_exports_every_declared_symbol(cuda_lib):
     from trajectories import _native
 
     assert declared == set(_native.EXPORTS)
-    assert cuda_lib.cmt_version() == 100
-    assert C.sizeof(_native.Element) == 88 and C.sizeof(_native.Source) == 80 and C.sizeof(_native.Outputs) == 72
+    assert cuda_lib.cmt_version() == 101
+    assert C.sizeof(_native.Element) == 88 and C.sizeof(_native.Source) == 80 and C.sizeof(_native.Outputs) == 80
 
 
 def test_abi_argument_validation(cuda_lib):
