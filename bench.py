@@ -45,9 +45,9 @@ UNIT = "molecules/s"
 WORKLOAD = ("configs[1]: examples/lens_simulation_beamline.py full CeNTREX beamline with ElectrostaticLens, "
             "J=2 mJ=0 Stark curve at 27.6 kV, CeNTREX velocity/position distributions")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload at
-# 1e7 molecules (profiles/r01_full_f_segments.txt); scaled linearly when --molecules differs
-NCU_TRAFFIC_LENS_1E7 = 13.2e6            # four segment launches + tail: 3.52 + 2.78 + 2.42 + 2.25 + 2.21 MB read
-NCU_TRAFFIC_WALK_1E7 = 514.4e6 + 12.9e6
+# 1e7 molecules (profiles/r02_full_step.txt); scaled linearly when --molecules differs
+NCU_TRAFFIC_LENS_1E7 = 13.2e6            # four segment launches + tail: 3.52 + 2.77 + 2.41 + 2.25 + 2.21 MB read
+NCU_TRAFFIC_WALK_1E7 = 517.0e6 + 13.4e6
 # smsp__inst_executed_pipe_fp64.sum over the launches of one 1e7-molecule step (walk + 4 segments + tail), ncu
 NCU_FP64_WARP_INST_STEP_1E7 = 1.2646e8     # profiles/r02_fp64_inst.csv: 0.64 (walk) + 40.47 + 31.83 + 27.62 + 25.77 (segments) + 0.13 (tail) million
 # algorithmic work per unit
@@ -231,6 +231,33 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_near_gpu(index: int):
+    """Restrict this process to the CPUs of the GPU's own NUMA node, so that the pinned host buffers of the e2e leg
+    are allocated in the memory next to the PCIe root the GPU hangs on (with several ranks per box the H2D streams
+    otherwise share one socket's memory and the inter-socket link).  Returns (previous affinity, description)."""
+    try:
+        before = os.sched_getaffinity(0)
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        with open(dev + "/local_cpulist") as f:
+            spec = f.read().strip()
+        node = open(dev + "/numa_node").read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= before
+        if cpus and cpus != before:
+            os.sched_setaffinity(0, cpus)
+        return before, {"numa_node": node, "cpus_bound": len(cpus) or len(before), "cpus_before": len(before)}
+    except Exception as exc:      # no NVML, no sysfs entry, not Linux: run unbound
+        return None, {"unbound": type(exc).__name__}
+
+
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
@@ -248,6 +275,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the propagation path has no CPU fallback")
+    affinity_before, numa = bind_near_gpu(local)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -434,7 +462,7 @@ def run_ours(args):
         "fp64_pipe_busy": fp64_cycles / (step_ms * 1e-3 * sm_mhz * 1e6),
         "fp64_pipe_busy_source": "derived: smsp__inst_executed_pipe_fp64.sum of one step's launches (ncu, profiles/r02_*) x 2 cycles per warp "
                                  "instruction / (592 sub-partitions x SM clock x ms_per_step)",
-        "traffic": NCU_TRAFFIC_LENS_1E7 * n / 1e7, "traffic_source": "profiles/r01_full_f_segments.txt (ncu --set full, summed over the stage's launches)",
+        "traffic": NCU_TRAFFIC_LENS_1E7 * n / 1e7, "traffic_source": "profiles/r02_full_step.txt (ncu --set full, summed over the stage's launches)",
         "peak_source": "measured live: cmt_fp64_peak DFMA stream (no FP64 figure in MEASURED_PEAKS.json)",
         "dadd_peak_tops": dadd.value / 1e12,
     }
@@ -450,7 +478,7 @@ def run_ours(args):
     roofline_walk = {
         "kernel": "walk_kernel<ic>", "bound": "hbm", "achieved": walk_gbs, "peak": hbm_peak, "unit": "GB/s",
         "frac": (walk_gbs / hbm_peak) if walk_gbs else None, "traffic": NCU_TRAFFIC_WALK_1E7 * n / 1e7,
-        "traffic_source": "profiles/r01_full_f_segments.txt (ncu --set full)", "peak_source": hbm_src,
+        "traffic_source": "profiles/r02_full_step.txt (ncu --set full)", "peak_source": hbm_src,
         "algorithmic_bytes_per_launch": BYTES_PER_MOLECULE * n, "avg_launch_ms": walk_ms,
         "share_of_step": walk_ms / (ms_seq / args.steps) if ms_seq > 0 else None,
         "algorithmic_flop_per_launch": flop_rows,
@@ -535,6 +563,8 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        if affinity_before:
+            os.sched_setaffinity(0, affinity_before)      # the CPU baseline gets every host core back
         r = cpu_rate(bl, vdist, xdist, target_s=12.0)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": f"{r['n']} molecules of the same workload ({r['seconds']:.1f} s): Philox source + propagation + Counter, oracle/cmt_oracle.c with OpenMP",
@@ -566,6 +596,7 @@ def run_ours(args):
             "roofline": roofline, "roofline_one_stream": roofline_one_stream, "roofline_walk": roofline_walk,
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "host_binding": numa,
             "counters": dict(zip(prop.flat.fate_names, counters.tolist())),
             "work_per_step": {"ballistic_rows": int(work[0]), "lens_rk_steps": int(work[1]),
                               "table_out_of_range": int(work[2]), "lens_entries": int(work[3]),
