@@ -544,7 +544,7 @@ def run_ours(args):
 
     sim = TrajectorySimulator(device=local, seed=seed)
     api_steps = max(1, min(args.steps, 5))
-    for _ in range(4):   # reach the steady state of the pinned result blocks (the first runs allocate them: ~45 ms each)
+    for _ in range(6):   # reach the steady state of the pinned result blocks (the first runs allocate them: ~45 ms each)
         sim.run_simulation(bl, "bench", N_traj=n, apertures_of_interest=["Detected"], n_jobs=10)
     barrier()
     api_calls = []
