@@ -620,7 +620,7 @@ def main():
     ap.add_argument("--no-reference-python", action="store_true", help="skip timing the unmodified Python reference (baseline/_ref)")
     ap.add_argument("--no-overlap", action="store_true", help="issue every step on one stream")
     ap.add_argument("--no-contracted", action="store_true", help="skip the contracted-arithmetic pass")
-    ap.add_argument("--slots", type=int, default=4, help="streams the overlapped steps alternate over")
+    ap.add_argument("--slots", type=int, default=6, help="streams the overlapped steps alternate over")
     ap.add_argument("--no-graphs", action="store_true", help="launch the overlapped steps individually instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -715,6 +715,10 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
         if (walk_ctas <= 0) {
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&walk_ctas, fn, WALK_THREADS, 0));
             if (!philox && !pair_mode) walk_ctas = std::min(walk_ctas, 14);
+            // beside a lens stage (another stream's, or the other half of the same run) eight walk CTAs per SM do as
+            // well as a full wave and leave the integrator's CTAs their registers: lone Philox run of 1e7 molecules
+            // 0.618 -> 0.584 ms, overlapped replay step unchanged (profiles/README.md, round 2)
+            if (has_lens) walk_ctas = std::min(walk_ctas, 8);
             walk_ctas = std::max(walk_ctas, 1);
         }
         const int grid_walk = (int)std::min<int64_t>(tiles, (int64_t)bl->n_sm * walk_ctas);

@@ -374,7 +374,10 @@ constexpr int LENS_SEGMENT_STEPS = 150;   // RK steps per launch (measured: 75..
 #define CMT_LENS_UNROLL 1
 #endif
 constexpr int LENS_UNROLL = CMT_LENS_UNROLL;   // RK steps per trip of the segment loop
-constexpr int LENS_SEG_GRID_CTAS = 3;     // CTAs per SM one launch asks for: leaves room for the next step's walk CTAs
+constexpr int LENS_SEG_GRID_CTAS = 2;     // CTAs per SM one launch asks for; its warps take further groups from the queue's cursor.
+                                          // Measured with the replicated table (round 2, 1e7 molecules): 1 / 2 / 3 / 4 CTAs per SM ->
+                                          // lens stage alone 0.565 / 0.431 / 0.467 / 0.499 ms, overlapped step 0.356 / 0.345 / 0.347 / 0.348 ms,
+                                          // lone Philox run 0.636 / 0.584 / 0.590 / 0.592 ms
 #ifndef LENS_SEG_MIN_CTAS
 #define LENS_SEG_MIN_CTAS 4               // register budget: 128 per thread (124 used): nothing spilled or rematerialised inside the
                                           // step loop.  Measured against 5 (96 registers) and 6 (80) with the one-record RK step:
