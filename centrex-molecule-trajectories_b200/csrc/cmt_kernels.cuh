@@ -25,7 +25,10 @@
 namespace cmt {
 
 constexpr int WALK_THREADS = 64;   // small CTAs fit next to resident lens CTAs of another stream (measured: 256 -> 64 gives +3 % overlapped)
-constexpr int LENS_THREADS = 128;
+#ifndef CMT_LENS_THREADS
+#define CMT_LENS_THREADS 128
+#endif
+constexpr int LENS_THREADS = CMT_LENS_THREADS;
 constexpr int TRAJ_THREADS = 64;
 constexpr int QUEUE_COMPONENTS = 8;  // x,y,z,vx,vy,vz,t + global index bits
 
