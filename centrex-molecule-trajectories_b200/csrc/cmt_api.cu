@@ -940,14 +940,17 @@ extern "C" int cmt_plane_crossings(const cmt_beamline_t *bl, int64_t n, const do
 // caller's buffers (truly asynchronous when those are pinned, still correct
 // when they are pageable).  H2D of chunk k+1 overlaps the kernels of chunk k.
 // ---------------------------------------------------------------------------
+constexpr int PIPE_SLOTS = 2;   // streams (each with its own buffers and queue workspace) consecutive chunks rotate over; measured
+                                // with 4 (round 2): host-IC path 1.106e9 against 1.102e9 molecules/s (the PCIe link is the bound),
+                                // a lone Philox run in 3 / 4 pieces on 3 / 4 streams 0.626 / 0.636 ms against 0.583 ms in two
 struct HostPipe {
     int device = -1;
     int64_t chunk = 0;
-    cudaStream_t st[2] = {nullptr, nullptr};
-    double *d_ic[2] = {nullptr, nullptr};
-    uint8_t *d_fate[2] = {nullptr, nullptr};
-    double *d_final[2] = {nullptr, nullptr};
-    void *d_ws[2] = {nullptr, nullptr};
+    cudaStream_t st[PIPE_SLOTS] = {};
+    double *d_ic[PIPE_SLOTS] = {};
+    uint8_t *d_fate[PIPE_SLOTS] = {};
+    double *d_final[PIPE_SLOTS] = {};
+    void *d_ws[PIPE_SLOTS] = {};
     size_t ws_bytes = 0;
     int64_t *d_cnt = nullptr;   // [CMT_MAX_FATES + CMT_WORK_SLOTS]
 
@@ -955,7 +958,7 @@ struct HostPipe {
     {
         if (device < 0) return;
         DeviceGuard guard(device);
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < PIPE_SLOTS; ++k) {
             if (st[k]) cudaStreamDestroy(st[k]);
             cudaFree(d_ic[k]); cudaFree(d_fate[k]); cudaFree(d_final[k]); cudaFree(d_ws[k]);
             st[k] = nullptr; d_ic[k] = nullptr; d_fate[k] = nullptr; d_final[k] = nullptr; d_ws[k] = nullptr;
@@ -973,7 +976,7 @@ namespace {
 
 int pipe_allocate(HostPipe &p, int64_t chunk, bool keep_ic, bool keep_fate, bool keep_final)
 {
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < PIPE_SLOTS; ++k) {
         CUDA_TRY(cudaStreamCreateWithFlags(&p.st[k], cudaStreamNonBlocking));
         CUDA_TRY(cudaMalloc(&p.d_ws[k], p.ws_bytes));
         if (keep_ic) CUDA_TRY(cudaMalloc(&p.d_ic[k], (size_t)6 * chunk * sizeof(double)));
@@ -1008,7 +1011,7 @@ int pipe_prepare(HostPipe &p, const cmt_beamline_t *bl, int64_t chunk, bool want
 
 int pipe_collect(HostPipe &p, const cmt_beamline_t *bl, int64_t *counters_host, int64_t *work_host)
 {
-    for (int k = 0; k < 2; ++k) CUDA_TRY(cudaStreamSynchronize(p.st[k]));
+    for (int k = 0; k < PIPE_SLOTS; ++k) CUDA_TRY(cudaStreamSynchronize(p.st[k]));
     int64_t h[CMT_MAX_FATES + CMT_WORK_SLOTS];
     CUDA_TRY(cudaMemcpy(h, p.d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
     for (int f = 0; f < bl->P.n_fates; ++f) counters_host[f] += h[f];
@@ -1040,8 +1043,9 @@ extern "C" int cmt_run_host_ic(const cmt_beamline_t *bl, int64_t n, const double
 
     const size_t dpitch = (size_t)p.chunk * sizeof(double), hpitch = (size_t)n * sizeof(double);
     const int64_t n_chunks = (n + chunk - 1) / chunk;
+    static const int ic_slots = std::max(1, std::min(PIPE_SLOTS, env_int("CMT_TUNE_IC_SLOTS", PIPE_SLOTS)));   // experiments only
     for (int64_t ci = 0; ci < n_chunks; ++ci) {
-        const int k = (int)(ci & 1);
+        const int k = (int)(ci % ic_slots);
         const int64_t off = ci * chunk, len = std::min<int64_t>(chunk, n - off);
         CUDA_TRY(cudaMemcpy2DAsync(p.d_ic[k], dpitch, ic_host + off, hpitch, (size_t)len * sizeof(double), 6,
                                    cudaMemcpyHostToDevice, p.st[k]));
@@ -1083,7 +1087,8 @@ extern "C" int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t 
     // 128 us each whatever their load).  Results do not depend on the cut: the source is indexed by the
     // global molecule number.
     int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 26);
-    if (n <= chunk && n >= ((int64_t)1 << 21)) chunk = (n + 1) / 2;
+    static const int tune_pieces = env_int("CMT_TUNE_PHILOX_PIECES", 2);          // experiments only
+    if (n <= chunk && n >= ((int64_t)1 << 21)) chunk = (n + tune_pieces - 1) / std::max(1, tune_pieces);
     if (const char *env = getenv("CMT_PHILOX_CHUNK")) {          // experiments only
         const long long v = atoll(env);
         if (v > 0) chunk = std::min<int64_t>(n, (int64_t)v);
@@ -1094,7 +1099,7 @@ extern "C" int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t 
     CUDA_TRY(cudaStreamSynchronize(p.st[0]));
     const int64_t n_chunks = (n + chunk - 1) / chunk;
     for (int64_t ci = 0; ci < n_chunks; ++ci) {
-        const int k = (int)(ci & 1);
+        const int k = (int)(ci % PIPE_SLOTS);
         const int64_t off = ci * chunk, len = std::min<int64_t>(chunk, n - off);
         cmt_outputs_t O;
         memset(&O, 0, sizeof(O));
