@@ -953,6 +953,8 @@ struct HostPipe {
     void *d_ws[PIPE_SLOTS] = {};
     size_t ws_bytes = 0;
     int64_t *d_cnt = nullptr;   // [CMT_MAX_FATES + CMT_WORK_SLOTS]
+    int64_t *h_cnt = nullptr;   // the same, page-locked: the one read-back of a run
+    cudaEvent_t ev[PIPE_SLOTS] = {};   // ordering between the slot streams without a host round trip
 
     void release()
     {
@@ -960,11 +962,15 @@ struct HostPipe {
         DeviceGuard guard(device);
         for (int k = 0; k < PIPE_SLOTS; ++k) {
             if (st[k]) cudaStreamDestroy(st[k]);
+            if (ev[k]) cudaEventDestroy(ev[k]);
+            ev[k] = nullptr;
             cudaFree(d_ic[k]); cudaFree(d_fate[k]); cudaFree(d_final[k]); cudaFree(d_ws[k]);
             st[k] = nullptr; d_ic[k] = nullptr; d_fate[k] = nullptr; d_final[k] = nullptr; d_ws[k] = nullptr;
         }
         cudaFree(d_cnt);
         d_cnt = nullptr;
+        if (h_cnt) cudaFreeHost(h_cnt);
+        h_cnt = nullptr;
         device = -1;
     }
     ~HostPipe() { release(); }
@@ -978,12 +984,14 @@ int pipe_allocate(HostPipe &p, int64_t chunk, bool keep_ic, bool keep_fate, bool
 {
     for (int k = 0; k < PIPE_SLOTS; ++k) {
         CUDA_TRY(cudaStreamCreateWithFlags(&p.st[k], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&p.ev[k], cudaEventDisableTiming));
         CUDA_TRY(cudaMalloc(&p.d_ws[k], p.ws_bytes));
         if (keep_ic) CUDA_TRY(cudaMalloc(&p.d_ic[k], (size_t)6 * chunk * sizeof(double)));
         if (keep_fate) CUDA_TRY(cudaMalloc(&p.d_fate[k], (size_t)chunk));
         if (keep_final) CUDA_TRY(cudaMalloc(&p.d_final[k], (size_t)10 * chunk * sizeof(double)));
     }
     CUDA_TRY(cudaMalloc(&p.d_cnt, (CMT_MAX_FATES + CMT_WORK_SLOTS) * sizeof(int64_t)));
+    CUDA_TRY(cudaHostAlloc(&p.h_cnt, (CMT_MAX_FATES + CMT_WORK_SLOTS) * sizeof(int64_t), cudaHostAllocDefault));
     return CMT_OK;
 }
 
@@ -1009,11 +1017,27 @@ int pipe_prepare(HostPipe &p, const cmt_beamline_t *bl, int64_t chunk, bool want
     return rc;
 }
 
+// Start of a run: the run's Counter is cleared on slot 0 and the other slots wait for that on the device.
+int pipe_begin(HostPipe &p)
+{
+    CUDA_TRY(cudaMemsetAsync(p.d_cnt, 0, (CMT_MAX_FATES + CMT_WORK_SLOTS) * sizeof(int64_t), p.st[0]));
+    CUDA_TRY(cudaEventRecord(p.ev[0], p.st[0]));
+    for (int k = 1; k < PIPE_SLOTS; ++k) CUDA_TRY(cudaStreamWaitEvent(p.st[k], p.ev[0], 0));
+    return CMT_OK;
+}
+
+// End of a run: slot 0 waits for the other slots on the device, copies the Counter into page-locked memory, and the
+// host waits once.  (Buffers the caller handed in are complete then as well: every copy into them was queued on
+// one of the slots.)
 int pipe_collect(HostPipe &p, const cmt_beamline_t *bl, int64_t *counters_host, int64_t *work_host)
 {
-    for (int k = 0; k < PIPE_SLOTS; ++k) CUDA_TRY(cudaStreamSynchronize(p.st[k]));
-    int64_t h[CMT_MAX_FATES + CMT_WORK_SLOTS];
-    CUDA_TRY(cudaMemcpy(h, p.d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int k = 1; k < PIPE_SLOTS; ++k) {
+        CUDA_TRY(cudaEventRecord(p.ev[k], p.st[k]));
+        CUDA_TRY(cudaStreamWaitEvent(p.st[0], p.ev[k], 0));
+    }
+    CUDA_TRY(cudaMemcpyAsync(p.h_cnt, p.d_cnt, (CMT_MAX_FATES + CMT_WORK_SLOTS) * sizeof(int64_t), cudaMemcpyDeviceToHost, p.st[0]));
+    CUDA_TRY(cudaStreamSynchronize(p.st[0]));
+    const int64_t *h = p.h_cnt;
     for (int f = 0; f < bl->P.n_fates; ++f) counters_host[f] += h[f];
     if (work_host) for (int k = 0; k < CMT_WORK_SLOTS; ++k) work_host[k] += h[CMT_MAX_FATES + k];
     return CMT_OK;
@@ -1038,8 +1062,8 @@ extern "C" int cmt_run_host_ic(const cmt_beamline_t *bl, int64_t n, const double
     const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 21);
     int rc = pipe_prepare(p, bl, chunk, true, fate_host != nullptr, final_host != nullptr);
     if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(p.d_cnt, 0, (CMT_MAX_FATES + CMT_WORK_SLOTS) * sizeof(int64_t), p.st[0]));
-    CUDA_TRY(cudaStreamSynchronize(p.st[0]));
+    rc = pipe_begin(p);
+    if (rc) return rc;
 
     const size_t dpitch = (size_t)p.chunk * sizeof(double), hpitch = (size_t)n * sizeof(double);
     const int64_t n_chunks = (n + chunk - 1) / chunk;
@@ -1095,8 +1119,8 @@ extern "C" int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t 
     }
     int rc = pipe_prepare(p, bl, chunk, false, false, false);
     if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(p.d_cnt, 0, (CMT_MAX_FATES + CMT_WORK_SLOTS) * sizeof(int64_t), p.st[0]));
-    CUDA_TRY(cudaStreamSynchronize(p.st[0]));
+    rc = pipe_begin(p);
+    if (rc) return rc;
     const int64_t n_chunks = (n + chunk - 1) / chunk;
     for (int64_t ci = 0; ci < n_chunks; ++ci) {
         const int k = (int)(ci % PIPE_SLOTS);
