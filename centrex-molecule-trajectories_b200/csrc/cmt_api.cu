@@ -571,22 +571,25 @@ extern "C" size_t cmt_workspace_bytes(const cmt_beamline_t *bl, int64_t n_max)
 struct TimedLaunch {
     cudaEvent_t a, b;
     int kind;
+    cudaStream_t st;
 };
 static std::mutex g_time_mu;
-static bool g_time_on = false;
+static int g_time_level = 0;      // 0 off; 1 the stage timers (kinds 0..3); 2 also one timer per lens kernel (kinds 8..)
 static std::vector<TimedLaunch> g_time_pending;
 static double g_time_ms[4] = {0, 0, 0, 0};
 static int64_t g_time_n[4] = {0, 0, 0, 0};
 
+// kinds: 0 walk kernel, 1 lens stage (segment launches + tail), 2 trajectory / resume kernels, 3 reserved;
+// timeline only (level 2): 8 + k = lens segment k, 7 = tail kernel
 struct ScopedTimer {
     bool on;
     cudaEvent_t a, b;
     cudaStream_t st;
     int kind;
-    ScopedTimer(int kind_, cudaStream_t st_) : on(false), st(st_), kind(kind_)
+    ScopedTimer(int kind_, cudaStream_t st_, int level = 1) : on(false), st(st_), kind(kind_)
     {
         std::lock_guard<std::mutex> lk(g_time_mu);
-        on = g_time_on;
+        on = g_time_level >= level;
         if (on) {
             cudaEventCreate(&a);
             cudaEventCreate(&b);
@@ -598,7 +601,7 @@ struct ScopedTimer {
         if (on) {
             cudaEventRecord(b, st);
             std::lock_guard<std::mutex> lk(g_time_mu);
-            g_time_pending.push_back({a, b, kind});
+            g_time_pending.push_back({a, b, kind, st});
         }
     }
 };
@@ -606,8 +609,19 @@ struct ScopedTimer {
 extern "C" int cmt_timing_enable(int on)
 {
     std::lock_guard<std::mutex> lk(g_time_mu);
-    g_time_on = on != 0;
+    g_time_level = on < 0 ? 0 : on;
     return CMT_OK;
+}
+
+static void timing_fold(const TimedLaunch &t)
+{
+    float f = 0;
+    if (t.kind < 4 && cudaEventElapsedTime(&f, t.a, t.b) == cudaSuccess) {
+        g_time_ms[t.kind] += f;
+        g_time_n[t.kind] += 1;
+    }
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
 }
 
 extern "C" int cmt_timing_read(double ms[4], int64_t launches[4], int reset)
@@ -615,13 +629,7 @@ extern "C" int cmt_timing_read(double ms[4], int64_t launches[4], int reset)
     std::lock_guard<std::mutex> lk(g_time_mu);
     for (auto &t : g_time_pending) {
         cudaEventSynchronize(t.b);
-        float f = 0;
-        if (cudaEventElapsedTime(&f, t.a, t.b) == cudaSuccess) {
-            g_time_ms[t.kind] += f;
-            g_time_n[t.kind] += 1;
-        }
-        cudaEventDestroy(t.a);
-        cudaEventDestroy(t.b);
+        timing_fold(t);
     }
     g_time_pending.clear();
     for (int k = 0; k < 4; ++k) {
@@ -630,6 +638,42 @@ extern "C" int cmt_timing_read(double ms[4], int64_t launches[4], int reset)
         if (reset) { g_time_ms[k] = 0; g_time_n[k] = 0; }
     }
     return CMT_OK;
+}
+
+extern "C" int64_t cmt_timing_timeline(double *start_ms, double *end_ms, int32_t *kind, int32_t *stream_id, int64_t capacity)
+{
+    std::lock_guard<std::mutex> lk(g_time_mu);
+    if (g_time_pending.empty()) return 0;
+    for (auto &t : g_time_pending) cudaEventSynchronize(t.b);
+    // the earliest start is the origin: elapsed times against the first record, shifted by the minimum
+    const cudaEvent_t ref = g_time_pending.front().a;
+    std::vector<double> a(g_time_pending.size()), b(g_time_pending.size());
+    std::vector<cudaStream_t> streams;
+    double lo = 0.0;
+    for (size_t i = 0; i < g_time_pending.size(); ++i) {
+        float fa = 0, fb = 0;
+        cudaEventElapsedTime(&fa, ref, g_time_pending[i].a);
+        cudaEventElapsedTime(&fb, ref, g_time_pending[i].b);
+        a[i] = fa; b[i] = fb;
+        lo = std::min(lo, (double)fa);
+    }
+    int64_t n = 0;
+    for (size_t i = 0; i < g_time_pending.size(); ++i) {
+        const TimedLaunch &t = g_time_pending[i];
+        size_t sid = 0;
+        while (sid < streams.size() && streams[sid] != t.st) ++sid;
+        if (sid == streams.size()) streams.push_back(t.st);
+        if (n < capacity) {
+            if (start_ms) start_ms[n] = a[i] - lo;
+            if (end_ms) end_ms[n] = b[i] - lo;
+            if (kind) kind[n] = t.kind;
+            if (stream_id) stream_id[n] = (int32_t)sid;
+        }
+        ++n;
+        timing_fold(t);
+    }
+    g_time_pending.clear();
+    return n;
 }
 
 // ---------------------------------------------------------------------------
@@ -784,14 +828,20 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
             A.cursor = A.count + 1;
             B.count = Q.count + 4 + 2 * k;
             B.cursor = B.count + 1;
-            CUDA_TRY(cudaLaunchKernelEx(&cfg, seg_fn[contract][copies_log2], bl->P, first_index, *out, A, B, X, seg));
+            {
+                ScopedTimer tk(8 + k, st, 2);
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, seg_fn[contract][copies_log2], bl->P, first_index, *out, A, B, X, seg));
+            }
             count_launch();
         }
         const int grid_tail = (int)std::min<int64_t>((n + TRAJ_THREADS - 1) / TRAJ_THREADS, (int64_t)bl->n_sm * 8);
         using TailFn = void (*)(const Params, int64_t, const cmt_outputs_t, Queue);
         static const TailFn tail[2][2] = {{tail_kernel<false, false>, tail_kernel<false, true>},
                                           {tail_kernel<true, false>, tail_kernel<true, true>}};
-        tail[contract][bl->has_mesh]<<<grid_tail, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, first_index, *out, X);
+        {
+            ScopedTimer tk(7, st, 2);
+            tail[contract][bl->has_mesh]<<<grid_tail, TRAJ_THREADS, bl->tab_bytes, st>>>(bl->P, first_index, *out, X);
+        }
         count_launch();
     }
     CUDA_TRY(cudaGetLastError());

@@ -93,6 +93,8 @@ _SIGNATURES = {
                                       C.c_void_p, C.c_void_p]),
     "cmt_timing_enable": (C.c_int, [C.c_int]),
     "cmt_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
+    "cmt_timing_timeline": (C.c_int64, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                        C.POINTER(C.c_int32), C.c_int64]),
     "cmt_launch_count": (C.c_int64, [C.c_int]),
     "cmt_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cmt_selftest": (C.c_int, [C.c_int, C.c_int64, C.c_uint64, C.c_int, C.POINTER(C.c_int64)]),

@@ -247,6 +247,13 @@ int cmt_run_host_philox(const cmt_beamline_t *bl, const cmt_source_t *src, uint6
  * kernel, ms[3] = source-only kernel; launches[k] = number of timed intervals. */
 int cmt_timing_enable(int on);
 int cmt_timing_read(double ms[4], int64_t launches[4], int reset);
+/* Measurement aid: with cmt_timing_enable(2) every kernel of the lens stage is bracketed by its own pair of events as
+ * well; this call waits for all recorded intervals and returns them -- start and end in ms after the earliest start,
+ * kind (0 walk kernel, 1 lens stage as a whole, 2 trajectory / resume kernels, 7 tail kernel, 8 + k lens segment k)
+ * and a small id of the stream they ran on -- up to `capacity` entries; the return value is the number recorded.
+ * The stage sums of cmt_timing_read are updated as well.  What overlapped with what, without a system profiler. */
+int64_t cmt_timing_timeline(double *start_ms, double *end_ms, int32_t *kind, int32_t *stream_id, int64_t capacity);
+
 
 /* Kernel launches this library has issued in the process so far (walk, lens segments, tail, source);
  * reset != 0 also sets the count back to zero. */
