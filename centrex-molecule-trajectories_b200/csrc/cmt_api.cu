@@ -759,10 +759,11 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
         if (walk_ctas <= 0) {
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&walk_ctas, fn, WALK_THREADS, 0));
             if (!philox && !pair_mode) walk_ctas = std::min(walk_ctas, 14);
-            // beside a lens stage (another stream's, or the other half of the same run) eight walk CTAs per SM do as
-            // well as a full wave and leave the integrator's CTAs their registers: lone Philox run of 1e7 molecules
-            // 0.618 -> 0.584 ms, overlapped replay step unchanged (profiles/README.md, round 2)
-            if (has_lens) walk_ctas = std::min(walk_ctas, 8);
+            // Philox launches (18 CTAs per SM would fit): beside a lens stage -- the other half of the same run --
+            // eight walk CTAs per SM do as well as a full wave and leave the integrator's CTAs their registers: lone
+            // run of 1e7 molecules 0.618 -> 0.584 ms (profiles/README.md, round 2).  Replay launches keep their full
+            // wave of 10: alone the kernel is HBM-bound (0.091 against 0.098 ms), overlapped it makes no difference.
+            if (has_lens && philox) walk_ctas = std::min(walk_ctas, 8);
             walk_ctas = std::max(walk_ctas, 1);
         }
         const int grid_walk = (int)std::min<int64_t>(tiles, (int64_t)bl->n_sm * walk_ctas);
