@@ -794,10 +794,10 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
         // step's walk CTAs, which fill what is left (measured: 0.549 -> 0.527 ms per step).
         ScopedTimer tm(1, st);
         static const int tune_seg = env_int("CMT_TUNE_SEG", LENS_SEGMENT_STEPS);          // experiments only
-        static const int tune_seg_ctas = env_int("CMT_TUNE_SEG_CTAS", 0);                 // experiments only
-        // a launch that has to fill the chip on its own (a 2^26-molecule chunk of a large run: ~360 000 molecules in
-        // the lens queue) takes every CTA the registers admit; smaller launches overlap with their neighbours'
-        const int seg_per_sm = tune_seg_ctas > 0 ? tune_seg_ctas : (n > ((int64_t)1 << 24) ? LENS_SEG_MIN_CTAS : LENS_SEG_GRID_CTAS);
+        // (a lone launch of 8e7 molecules would like 4 CTAs per SM -- FP64 pipe 75 % against 68 % -- but the 2^26-molecule
+        // chunks of a large run overlap with their neighbours on the other streams like small ones do: 1e10 molecules
+        // through run_simulation take 0.406 / 0.403 / 0.424 s with 2 / 3 / 4, profiles/experiments/r02x_*.log)
+        static const int seg_per_sm = env_int("CMT_TUNE_SEG_CTAS", LENS_SEG_GRID_CTAS);   // experiments only
         const bool contract = bl->math == CMT_MATH_CONTRACTED;
         int least = 0, greatest = 0;
         if (tune_lens_prio) cudaDeviceGetStreamPriorityRange(&least, &greatest);

@@ -2,7 +2,7 @@
 """Run the BASELINE.json configurations end to end through the public API on one B200 and print
 one JSON object per configuration (wall clock around run_simulation, as a user sees it).
 
-    python profiles/run_configs.py > profiles/r01_configs.jsonl
+    python profiles/run_configs.py > profiles/r02_configs.jsonl
 """
 import json
 import sys
@@ -67,6 +67,16 @@ def main():
                 total += sum(sim.counter.counter_dict.values())
         return dict(molecules=total, efficiency=eff, runs=len(eff))
     timed("configs[2] 8 states x 5 voltages x 1e7 molecules, detected trajectories saved", c3)
+
+    def c3s():
+        states = [1 * UncoupledBasisState(J=J, mJ=mJ, I1=1 / 2, m1=1 / 2, I2=1 / 2, m2=1 / 2, Omega=0, P=(-1) ** J,
+                                          electronic_state="X")
+                  for J, mJ in [(0, 0), (1, 0), (1, 1), (2, 0), (2, 1), (2, 2), (3, 0), (3, 1)]]
+        res = sim.run_sweep(lens_beamline(), states, [21e3, 25e3, 28.6e3, 31e3, 35e3], N_traj=int(1e7), n_jobs=10)
+        return dict(molecules=sum(sum(r.counter.counter_dict.values()) for r in res.values()), runs=len(res),
+                    efficiency={f"J={k[0]},mJ={k[1]},V={k[2] / 1e3:g}kV": r.counter.calculate_efficiency() for k, r in res.items()})
+    timed("configs[2] as ONE run_sweep call, Counters only, 40 Stark tables (full Hamiltonian) built inside the call", c3s)
+    timed("configs[2] as ONE run_sweep call again (Stark curves cached)", c3s)
 
     def c4():
         sim.run_simulation(spa_beamline(), "c4", N_traj=int(1e9), apertures_of_interest=["Detected"], n_jobs=9,
