@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Parity of the CUDA path with the CPU oracle at sizes beyond the test suite (round 1).
+"""Parity of the CUDA path with the CPU oracle at sizes beyond the test suite.
 
-    python profiles/parity_at_scale.py > profiles/r01_parity_at_scale.json
+    python profiles/parity_at_scale.py > profiles/r02_parity_at_scale.json
 """
 import json
 import sys
