@@ -237,12 +237,18 @@ def bind_near_gpu(index: int):
     otherwise share one socket's memory and the inter-socket link).  Returns (previous affinity, description)."""
     try:
         before = os.sched_getaffinity(0)
-        import pynvml
+        try:        # the CUDA device's own PCI address (NVML's enumeration order need not be CUDA's)
+            import torch
 
-        pynvml.nvmlInit()
-        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
-        bus = bus.decode() if isinstance(bus, bytes) else bus
-        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+            pr = torch.cuda.get_device_properties(index)
+            bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        except Exception:
+            import pynvml
+
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()[-12:]
+        dev = "/sys/bus/pci/devices/" + bus
         with open(dev + "/local_cpulist") as f:
             spec = f.read().strip()
         node = open(dev + "/numa_node").read().strip()

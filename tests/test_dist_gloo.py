@@ -171,3 +171,41 @@ def test_identically_seeded_ranks_draw_disjoint_pieces():
     firsts = {p[0][0, 0] for p in pieces}
     assert len(firsts) == loops                      # no chunk twice
     assert list(eng.owned_draws(CeNTREXVelocityDistribution(), Shifted(), 0, loops, 0, 1)) == []
+
+
+def _merge_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    for p in (str(ROOT), str(ROOT / "centrex-molecule-trajectories_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import json
+
+    import torch.distributed as dist
+
+    from trajectories import _hybrid
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # a user element is free to invent fate names: the ranks need not have met the same ones
+    mine = {"4K shield": 10 + rank, "Detected": 3} if rank == 0 else {"4K shield": 10 + rank, "scattered away": 7}
+    merged = _hybrid.merge_counts_across_ranks(dict(mine))
+    (Path(out_dir) / f"merged{rank}.json").write_text(json.dumps(merged, sort_keys=True))
+    dist.destroy_process_group()
+
+
+def test_hybrid_counter_merge_world2(tmp_path):
+    """Mixed beamlines (user-defined elements) keep their Counter as name -> count on the host; under
+    torch.distributed the dictionaries of all ranks are summed by name on every rank."""
+    import json
+
+    import torch.multiprocessing as mp
+
+    from trajectories import _hybrid
+
+    assert _hybrid.merge_counts_across_ranks({"a": 1}) == {"a": 1}          # no process group: unchanged
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_merge_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    want = {"4K shield": 21, "Detected": 3, "scattered away": 7}
+    for rank in (0, 1):
+        assert json.loads((tmp_path / f"merged{rank}.json").read_text()) == want
