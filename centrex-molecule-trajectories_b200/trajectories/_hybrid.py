@@ -164,10 +164,13 @@ class HybridRun:
             if alive.numel() == 0:
                 break
             if isinstance(stage, _DeviceStage):
+                last = None
                 if state is None:
+                    # the normal launch, fates only (so the FP32 filter of the walk kernel stays on); the last rows of
+                    # the few survivors follow below from a resume launch on just those
                     stage.prop.reset()
-                    res = stage.prop.propagate_ic(ic, want_fate=True, want_final=True)
-                    fate, last = res.fate, res.final
+                    res = stage.prop.propagate_ic(ic, want_fate=True)
+                    fate = res.fate
                     self.work += res.work.cpu().numpy()
                 else:
                     fate, last = _resume(stage.prop, state)
@@ -187,7 +190,16 @@ class HybridRun:
                             end_name[int(j)] = stage.names[int(f)]
                         end_stage[idx[~keep]] = -1            # of no interest
                 sel = going.nonzero().squeeze(1)
-                alive, state = alive[sel], last[:, sel].contiguous()
+                if last is None:
+                    start = torch.zeros((10, sel.numel()), dtype=torch.float64, device=self.tdev)
+                    start[0:6] = ic[:, sel]
+                    start[7] = -eng.G
+                    again, state = _resume(stage.prop, start)
+                    if sel.numel() and not bool((again == stage.alive_id).all()):
+                        raise RuntimeError("resume launch disagrees with the propagation launch about a survivor")
+                else:
+                    state = last[:, sel].contiguous()
+                alive = alive[sel]
                 continue
 
             # ---- host stage: the user's element, on the molecules that reach it ----
