@@ -26,6 +26,7 @@ are one batched product; only the composition of the permutations runs in a Pyth
 """
 from __future__ import annotations
 
+import threading
 from dataclasses import dataclass
 from functools import lru_cache
 from typing import Dict, List, Tuple
@@ -127,6 +128,54 @@ def _block(two_mF: int, j_max: int, consts: XConstants):
     return idx, H_ff[sub], H_S[sub], H_Z[sub]
 
 
+# The eigenpairs of a block and their re-ordering depend on the block and on the field values only, not on which
+# of the block's states is followed: a sweep over states (examples/lens_simulation_different_states.py) asks for the
+# same (block, field grid) once per state.  The followed energies of ALL states of a block are therefore computed
+# once and kept; threads that ask for the same key wait for the first one instead of repeating its work.
+_FOLLOWED: Dict[tuple, tuple] = {}
+_FOLLOWED_LOCKS: Dict[tuple, "threading.Lock"] = {}
+_FOLLOWED_GUARD = threading.Lock()
+_FOLLOWED_MAX = 64
+
+
+def _followed_block(two_mF: int, flat: np.ndarray, Bz: float, E_ref: float, j_max: int, consts: XConstants):
+    """(idx, V_ref0, followed): the block's basis indices, its eigenvectors at E_ref, and followed[i, c] = the energy
+    at field i of the adiabatic state that is column c of the reference set (stark_potential.py:27-55)."""
+    key = (two_mF, flat.tobytes(), float(Bz), float(E_ref), j_max, consts)
+    hit = _FOLLOWED.get(key)
+    if hit is not None:
+        return hit
+    with _FOLLOWED_GUARD:
+        lock = _FOLLOWED_LOCKS.setdefault(key, threading.Lock())
+    with lock:
+        hit = _FOLLOWED.get(key)
+        if hit is not None:
+            return hit
+        idx, H0, HS, HZ = _block(two_mF, j_max, consts)
+        base = H0 + Bz * HZ
+        _, V_ref0 = np.linalg.eigh(base + E_ref * HS)
+        energies, vecs = np.linalg.eigh(base[None, :, :] + flat[:, None, None] * HS[None, :, :])
+        # raw overlaps |V_i^T V_{i-1}| (and with the reference set for the first field value), all at once
+        prev = np.concatenate([V_ref0[None, :, :], vecs[:-1]], axis=0)
+        best = np.argmax(np.abs(np.matmul(vecs.transpose(0, 2, 1), prev)), axis=2)    # [n_E, nb]: column of prev per row
+        nb = len(idx)
+        followed = np.empty((flat.size, nb))
+        inv_perm = np.arange(nb)        # position of raw column c of the previous set inside its re-ordered form
+        for i in range(flat.size):
+            # reorder_evecs: index = argsort(argmax(overlap with the RE-ORDERED previous set, axis=1))
+            index = np.argsort(inv_perm[best[i]], kind="quicksort")
+            followed[i] = energies[i, index]
+            inv_perm = np.empty(nb, dtype=np.int64)
+            inv_perm[index] = np.arange(nb)
+        hit = (idx, V_ref0, followed)
+        with _FOLLOWED_GUARD:
+            if len(_FOLLOWED) >= _FOLLOWED_MAX:
+                _FOLLOWED.clear()
+                _FOLLOWED_LOCKS.clear()
+            _FOLLOWED[key] = hit
+        return hit
+
+
 def follow_state(J: int, mJ: int, m1: float, m2: float, Ez_V_per_cm, Bz: float = 1e-4, E_ref: float = 100.0,
                  j_max: int = J_MAX, consts: XConstants = XConstants()) -> np.ndarray:
     """Energy (Hz) of the adiabatic state that is closest to |J, mJ, m1, m2> at E_ref, at every field of
@@ -135,30 +184,15 @@ def follow_state(J: int, mJ: int, m1: float, m2: float, Ez_V_per_cm, Bz: float =
     if not (0 <= J <= j_max and abs(mJ) <= J and abs(m1) == 0.5 and abs(m2) == 0.5):
         raise ValueError(f"not a state of the basis: J={J}, mJ={mJ}, m1={m1}, m2={m2} (J <= {j_max})")
     QN = operators(j_max, consts)[0]
-    idx, H0, HS, HZ = _block(int(round(2 * (mJ + m1 + m2))), j_max, consts)
-    me = int(np.nonzero(idx == QN.index((J, mJ, float(m1), float(m2))))[0][0])
     Ez = np.asarray(Ez_V_per_cm, dtype=np.float64)
-    flat = Ez.reshape(-1)
-    base = H0 + Bz * HZ
-    _, V_ref0 = np.linalg.eigh(base + E_ref * HS)
-    # find_closest_vector_idx: the reference eigenvector with the largest overlap with the basis state
-    col = int(np.argmax(np.abs(V_ref0[me, :])))
+    flat = np.ascontiguousarray(Ez.reshape(-1))
     if flat.size == 0:
         return np.zeros(Ez.shape)
-    energies, vecs = np.linalg.eigh(base[None, :, :] + flat[:, None, None] * HS[None, :, :])
-    # raw overlaps |V_i^T V_{i-1}| (and with the reference set for the first field value), all at once
-    prev = np.concatenate([V_ref0[None, :, :], vecs[:-1]], axis=0)
-    best = np.argmax(np.abs(np.matmul(vecs.transpose(0, 2, 1), prev)), axis=2)    # [n_E, nb]: column of prev per row
-    nb = len(idx)
-    out = np.empty(flat.size)
-    inv_perm = np.arange(nb)            # position of raw column c of the previous set inside its re-ordered form
-    for i in range(flat.size):
-        # reorder_evecs: index = argsort(argmax(overlap with the RE-ORDERED previous set, axis=1))
-        index = np.argsort(inv_perm[best[i]], kind="quicksort")
-        out[i] = energies[i, index[col]]
-        inv_perm = np.empty(nb, dtype=np.int64)
-        inv_perm[index] = np.arange(nb)
-    return out.reshape(Ez.shape)
+    idx, V_ref0, followed = _followed_block(int(round(2 * (mJ + m1 + m2))), flat, Bz, E_ref, j_max, consts)
+    me = int(np.nonzero(idx == QN.index((J, mJ, float(m1), float(m2))))[0][0])
+    # find_closest_vector_idx: the reference eigenvector with the largest overlap with the basis state
+    col = int(np.argmax(np.abs(V_ref0[me, :])))
+    return followed[:, col].reshape(Ez.shape).copy()
 
 
 def stark_joule(J: int, mJ: int, m1: float, m2: float, Ez_V_per_cm, **kw) -> np.ndarray:

@@ -403,7 +403,8 @@ class TrajectorySimulator:
             seed = int(eng.broadcast_object(int(np.random.randint(0, 2**62))))
 
         # the Stark tables of all points, built side by side (each is a chain of small LAPACK calls that release
-        # the GIL), then one flattening per point, differing only in the lens table
+        # the GIL; points whose states share an mF block and a voltage share one set of eigenpairs, _tlf_full.py),
+        # then one flattening per point, differing only in the lens table
         def table_of(point):
             probe = shallow(lens)
             probe.state, probe.V, probe.a_interp = point[0], point[1], None
@@ -417,7 +418,7 @@ class TrajectorySimulator:
             one_blas_thread = threadpool_limits(1)
         except Exception:
             one_blas_thread = nullcontext()
-        with one_blas_thread, ThreadPoolExecutor(max_workers=max(1, min(len(points), os.cpu_count() or 1, 8))) as pool:
+        with one_blas_thread, ThreadPoolExecutor(max_workers=max(1, min(len(points), os.cpu_count() or 1, 16))) as pool:
             interps = list(pool.map(table_of, points))
         flats, keys, lenses = [], [], []
         saved_state, saved_V, saved_tab = lens.state, lens.V, lens.a_interp

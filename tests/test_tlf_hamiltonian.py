@@ -93,6 +93,28 @@ def test_blockwise_following_equals_the_reference_loop(state):
     assert np.max(np.abs(got - want)) < 1e-3, np.max(np.abs(got - want))
 
 
+def test_states_of_one_block_share_its_eigenpairs():
+    """A sweep over states asks for the same (mF block, field grid) once per state: the followed energies of the whole
+    block are computed once (threads that ask for the same block wait for the first) and every state reads its own
+    column -- the same numbers as a computation of its own."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    Ez = np.linspace(0.0, 31000.0, 222)
+    states = [(0, 0), (1, 0), (2, 0), (3, 0), (1, 1), (2, 1)]
+    alone = []
+    for J, mJ in states:
+        F._FOLLOWED.clear()
+        alone.append(F.follow_state(J, mJ, 0.5, -0.5, Ez))
+    F._FOLLOWED.clear()
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        shared = list(pool.map(lambda s: F.follow_state(s[0], s[1], 0.5, -0.5, Ez), states))
+    assert len(F._FOLLOWED) == 2                       # mF = 0 and mF = 1, one decomposition each
+    for a, b in zip(alone, shared):
+        assert np.array_equal(a, b)
+    shared[0][:] = 0.0                                 # callers get copies
+    assert np.array_equal(F.follow_state(0, 0, 0.5, -0.5, Ez), alone[0])
+
+
 def test_lens_table_full_vs_rigid():
     """How far the rigid-rotor table (fixtures, bench workload) is from the full-Hamiltonian one the lens builds."""
     mass = (204.38 + 19.00) * 1.67e-27
