@@ -21,6 +21,7 @@ DEFAULT_CHUNK = 1 << 26          # molecules per launch: larger launches keep th
                                  # 2 x 64 B per queue entry: 8.6 GB per stream slot if the queue is sized for every
                                  # molecule, 0.13 GB when it is sized from a pilot launch (Propagator.queue_capacity)
 PILOT_MOLECULES = 1 << 21        # first launch of a large Philox run: full-size queue, its lens-entry count sizes the rest
+SWEEP_PILOT_MOLECULES = 1 << 18  # run_sweep: a throw-away launch of the first point that sizes the queues of all points
 ROW_BUDGET_BYTES = 1 << 30       # device bytes per saved-trajectory batch
 PINNED_RESULT_BYTES = 2 << 30    # saved-trajectory blocks up to this size are returned in page-locked memory
 
@@ -242,6 +243,9 @@ class GraphedStep:
             self.graph.replay()
 
 
+_SLOT_STREAMS: dict = {}      # device index -> the side streams every Propagator of that device launches on
+
+
 class Propagator:
     """Reusable launch context: beamline handle + scratch buffers on one device.
 
@@ -324,10 +328,17 @@ class Propagator:
 
     # -- streams ---------------------------------------------------------------
     def _slot_stream(self, slot):
+        # The slot streams belong to the device, not to the Propagator: run_simulation makes a Propagator per call,
+        # and the caching allocator keeps freed blocks per stream -- with fresh streams every call the 128 B x n
+        # workspaces of a 1e7-molecule run were allocated from the driver again each time (0.5 ms per
+        # torch.empty, 1 ms of a 2 ms call; profiles/prof_api.py).
         torch = _torch()
         if self._streams is None:
+            pool = _SLOT_STREAMS.setdefault(self.device, [])
             with torch.cuda.device(self.device):
-                self._streams = [torch.cuda.Stream(device=self.tdev) for _ in range(self.n_slots)]
+                while len(pool) < self.n_slots:
+                    pool.append(torch.cuda.Stream(device=self.tdev))
+            self._streams = pool[:self.n_slots]
         return self._streams[slot % self.n_slots]
 
     def join(self):
@@ -514,7 +525,7 @@ class Propagator:
                 valid[where] = v
         return out, valid.bool(), fate
 
-    def trajectories(self, state, select=None, select_base=0):
+    def trajectories(self, state, select=None, select_base=0, defer_sync=False):
         """Full trajectories of the molecules in `state` ([6|10, m] device tensor), optionally gathered
         through `select` (global indices, device int64).
 
@@ -524,7 +535,10 @@ class Propagator:
         a detected one 613).  Rows come back through two reusable pinned staging buffers.
 
         Returns (rows [total_rows, 10], offsets [k + 1] int64, fate [k]) as host arrays; molecule j owns
-        rows[offsets[j]:offsets[j + 1]].
+        rows[offsets[j]:offsets[j + 1]].  With `defer_sync` a fourth item follows, a callable that waits for the rows
+        to have arrived: offsets and fates are final after the first pass, so the caller can build its per-molecule
+        objects (views of `rows`, 2 ms for 2385 molecules) while the device-to-host copy (2 ms for their 117 MB) is
+        still in flight, and call it before reading a row.
         """
         torch = _torch()
         n_comp = state.shape[0]
@@ -540,6 +554,7 @@ class Propagator:
         offsets = torch.zeros(k_total + 1, dtype=torch.int64, device=self.tdev)
         torch.cumsum(n_rows, 0, out=offsets[1:])
         off_np = offsets.cpu().numpy()
+        fate_np = fate.cpu().numpy()        # final after the counting pass (the second pass writes the same bytes)
         total_rows = int(off_np[-1])
         # Result block.  Up to PINNED_RESULT_BYTES it is page-locked memory from torch's caching host
         # allocator: the device copies straight into the array the caller receives (no staging, no
@@ -604,9 +619,16 @@ class Propagator:
                 piece += 1
             drain()                            # the device buffer is released before the next batch
             lo = hi
-        if host is not None:
-            torch.cuda.current_stream(self.device).synchronize()
-        return rows_out, off_np, fate.cpu().numpy()
+        if host is None:
+            wait = lambda: None                                 # the staged path has copied everything out already
+        else:
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(self.device))
+            wait = done.synchronize
+        if defer_sync:
+            return rows_out, off_np, fate_np, wait
+        wait()
+        return rows_out, off_np, fate_np
 
 
 _STAGING: Dict[int, list] = {}

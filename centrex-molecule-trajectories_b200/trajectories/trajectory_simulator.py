@@ -438,21 +438,37 @@ class TrajectorySimulator:
         chunk = prop.fit_chunk(self.chunk)
         if not save_mask and (1 << 21) <= hi - lo <= chunk:
             chunk = (hi - lo + 1) // 2
-        per_point, k = [], 0
-        for flat in flats:
-            prop.rebind(flat)
-            molecules: List[Molecule] = []
-            for first in range(lo, hi, chunk):
-                n = min(chunk, hi - first)
-                if not save_mask:
-                    prop.propagate_philox(source, seed, first, n, slot=k)
-                    k += 1
-                    continue
-                res = prop.propagate_philox(source, seed, first, n, save_mask=save_mask)
-                if res.saved_index.numel():
-                    molecules.extend(self._collect(prop, prop.draw(source, seed, index=res.saved_index)))
-            per_point.append((prop.counters, prop.work, molecules))
-        prop.join()
+        # How many molecules reach the lens does not depend on the lens table, so a small pilot launch of the first
+        # point sizes the lens queues of every launch of the sweep (128 B x n per stream slot otherwise: 1.9 GB of
+        # fresh device memory for 1e7-molecule points, 0.16 s of a first call); a queue that overflows all the same
+        # (work[6]) sends the whole sweep through full-size queues.
+        if hi - lo > 4 * eng.SWEEP_PILOT_MOLECULES:
+            prop.propagate_philox(source, seed, lo, eng.SWEEP_PILOT_MOLECULES)
+            prop.learn_entry_fraction(eng.SWEEP_PILOT_MOLECULES)
+
+        def launch_all():
+            per_point, k = [], 0
+            for flat in flats:
+                prop.rebind(flat)
+                molecules: List[Molecule] = []
+                for first in range(lo, hi, chunk):
+                    n = min(chunk, hi - first)
+                    if not save_mask:
+                        prop.propagate_philox(source, seed, first, n, slot=k)
+                        k += 1
+                        continue
+                    res = prop.propagate_philox(source, seed, first, n, save_mask=save_mask)
+                    if res.saved_index.numel():
+                        molecules.extend(self._collect(prop, prop.draw(source, seed, index=res.saved_index)))
+                per_point.append((prop.counters, prop.work, molecules))
+            prop.join()
+            return per_point
+
+        per_point = launch_all()
+        works = torch.stack([w for _, w, _ in per_point]).cpu().numpy()
+        if prop.entry_fraction is not None and works[:, 6].sum() > 0:
+            prop.entry_fraction = None
+            per_point = launch_all()
         counts = eng.allreduce_counts(torch.stack([c for c, _, _ in per_point])).cpu().numpy()
         works = eng.allreduce_counts(torch.stack([w for _, w, _ in per_point])).cpu().numpy()
         self.last_work = works.sum(axis=0)
@@ -570,13 +586,15 @@ class TrajectorySimulator:
     # -- helpers ----------------------------------------------------------------
     @staticmethod
     def _collect(prop: "eng.Propagator", ic, select=None) -> List[Molecule]:
-        rows, offsets, fate = prop.trajectories(ic, select=select)
+        rows, offsets, fate, rows_arrived = prop.trajectories(ic, select=select, defer_sync=True)
         names = prop.flat.fate_names
         from_rows = Molecule.from_rows
         lo = np.asarray(offsets).tolist()
-        # each trajectory is a view of its slice of the result block
+        # each trajectory is a view of its slice of the result block; the shells are built while the rows are
+        # still on their way from the device (nothing below reads a row before rows_arrived())
         mols = [from_rows(rows[lo[k]:lo[k + 1]], names[f], names[f] == "Detected")
                 for k, f in enumerate(np.asarray(fate).tolist())]
+        rows_arrived()
         # (a non-finite value poisons every later row of its trajectory, so the last rows tell)
         last = rows[np.asarray(lo[1:], dtype=np.int64) - 1] if len(lo) > 1 else rows[:0]
         if last.size and not np.isfinite(last).all():

@@ -31,3 +31,12 @@ for k in range(3):
     sim.run_simulation(bl, "r", N_traj=10_000_000, n_jobs=10)
     torch.cuda.synchronize()
     print("no saving", k, "%.2f ms" % (1e3 * (time.perf_counter() - t)), flush=True)
+for k in range(3):
+    sim.run_simulation(bl, "r", N_traj=10_000_000, n_jobs=10)
+pr = cProfile.Profile()
+pr.enable()
+for k in range(10):
+    sim.run_simulation(bl, "r", N_traj=10_000_000, n_jobs=10)
+pr.disable()
+print("ten Counter-only calls:")
+pstats.Stats(pr).sort_stats("tottime").print_stats(30)

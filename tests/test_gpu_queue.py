@@ -119,3 +119,28 @@ def test_run_simulation_pilot_and_fallback(torch_cuda, monkeypatch):
     assert len(small.result.molecules) == len(want.result.molecules) == want.counter.counter_dict["Detected"]
     for ma, mb in zip(small.result.molecules[::97], want.result.molecules[::97]):
         np.testing.assert_array_equal(ma.trajectory.x, mb.trajectory.x)
+
+
+def test_run_sweep_pilot_and_fallback(torch_cuda, monkeypatch):
+    """run_sweep sizes the lens queues of every point from one small pilot launch of the first point; the points are
+    what they are with full-size queues, and queues that overflow all the same send the sweep through full-size ones."""
+    from trajectories import _engine as eng
+    from trajectories.trajectory_simulator import TrajectorySimulator
+
+    bl = lens_beamline()
+    states, volts, n, seed = [(2, 0), (1, 1)], [24e3, 30e3], 4_000_000, 5
+    assert n > 4 * eng.SWEEP_PILOT_MOLECULES
+    sized = TrajectorySimulator(seed=seed).run_sweep(bl, states, volts, N_traj=n, n_jobs=10)
+    with monkeypatch.context() as mp:
+        mp.setattr(eng, "SWEEP_PILOT_MOLECULES", 1 << 40)           # no pilot: every queue holds every molecule
+        full = TrajectorySimulator(seed=seed).run_sweep(bl, states, volts, N_traj=n, n_jobs=10)
+    with monkeypatch.context() as mp:
+        mp.setattr(eng.Propagator, "queue_capacity", lambda self, m: int(m) if self.entry_fraction is None else 500)
+        sim = TrajectorySimulator(seed=seed)
+        again = sim.run_sweep(bl, states, volts, N_traj=n, n_jobs=10)
+        assert sim.last_work[6] == 0
+    assert set(sized) == set(full) == set(again) and len(sized) == 4
+    for key in full:
+        want = full[key].counter.counter_dict
+        assert sum(want.values()) == n
+        assert sized[key].counter.counter_dict == want and again[key].counter.counter_dict == want
