@@ -599,7 +599,7 @@ def run_ours(args):
                            "counters_match_device_run": philox_same},
             "e2e_api": {"value": api_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": rows_bytes + 8 * 16,
                         "path": "TrajectorySimulator.run_simulation(beamline, N_traj=n, apertures_of_interest=['Detected'], n_jobs=10): "
-                                "Philox source, Counter, and the detected molecules' full trajectories back as Molecule objects",
+                                "Philox source, Counter, and the detected molecules' full trajectories back on the host (result.molecules: Molecule views of the row block, made on access)",
                         "saved_molecules_per_step": n_saved, "steps": api_steps, "ms_per_call": api_calls,
                         "gc": "gc.freeze() after the warm-up calls (a full collection of the interpreter's import-time objects costs 35-40 ms every ~14 calls otherwise)"},
             "contracted_math": contracted,

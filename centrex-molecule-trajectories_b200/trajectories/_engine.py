@@ -556,19 +556,16 @@ class Propagator:
         off_np = offsets.cpu().numpy()
         fate_np = fate.cpu().numpy()        # final after the counting pass (the second pass writes the same bytes)
         total_rows = int(off_np[-1])
-        # Result block.  Up to PINNED_RESULT_BYTES it is page-locked memory from torch's caching host
-        # allocator: the device copies straight into the array the caller receives (no staging, no
-        # host-side copy, no first-touch page faults), and the block returns to the allocator's pool
-        # when the last Molecule viewing it is dropped, so a loop of runs re-uses the same pages.
-        # Larger results (or a failed page-lock) go through two reusable pinned staging buffers into
-        # ordinary memory.
-        host = None
+        # Result block.  Up to PINNED_RESULT_BYTES it is page-locked memory from a small pool (_pinned_rows): the
+        # device copies straight into the array the caller receives (no staging, no host-side copy, no first-touch
+        # page faults), and the block is free for the next run once the last trajectory viewing it has been dropped,
+        # so a loop of runs re-uses the same pages.  Larger results, results that find the pool busy, or a failed
+        # page-lock go through two reusable pinned staging buffers into ordinary memory.
+        host = rows_out = None
         if 0 < total_rows * nat.CMT_ROW_DOUBLES * 8 <= PINNED_RESULT_BYTES:
-            try:
-                host = torch.empty((total_rows, nat.CMT_ROW_DOUBLES), dtype=torch.float64, pin_memory=True)
-            except RuntimeError:
-                host = None
-        rows_out = host.numpy() if host is not None else np.empty((total_rows, nat.CMT_ROW_DOUBLES), dtype=np.float64)
+            host, rows_out = _pinned_rows(total_rows)
+        if host is None:
+            rows_out = np.empty((total_rows, nat.CMT_ROW_DOUBLES), dtype=np.float64)
 
         # pass 2: rows, in batches bounded by the device row budget
         stage = _staging(self.device) if host is None else None
@@ -629,6 +626,45 @@ class Propagator:
             return rows_out, off_np, fate_np, wait
         wait()
         return rows_out, off_np, fate_np
+
+
+# Page-locked result blocks.  Locking pages costs ~0.4 ms per MB (45 ms for the 117 MB of a 1e7-molecule run of the lens
+# beamline), far more than the copy it speeds up, so it only pays for memory that is used again: a loop of runs whose
+# previous result has been dropped.  The pool keeps at most PINNED_POOL_BLOCKS blocks; a block is free again when the
+# array handed out over it -- the base of every trajectory view of that result -- has been collected.  A result that
+# finds no free block while the pool is full (results that are all kept: the 16 launches of configs[3], a loop over
+# 40 sweep points) goes through the pinned staging buffers into ordinary memory instead, which is faster than locking
+# fresh pages for it.
+PINNED_POOL_BLOCKS = 3
+PINNED_BLOCK_GRAIN = 32 << 20
+_PINNED_POOL: list = []       # [block (uint8 tensor, page-locked), weakref to the array last handed out over it or None]
+
+
+def _pinned_rows(total_rows: int):
+    """(tensor [total_rows, 10] float64 over page-locked memory, the same memory as a NumPy array) or (None, None)."""
+    import weakref
+
+    torch = _torch()
+    nbytes = total_rows * nat.CMT_ROW_DOUBLES * 8
+    free = [e for e in _PINNED_POOL if e[1] is None or e[1]() is None]
+    fit = [e for e in free if e[0].numel() >= nbytes]
+    entry = min(fit, key=lambda e: e[0].numel()) if fit else None
+    if entry is None and (len(_PINNED_POOL) < PINNED_POOL_BLOCKS or free):
+        if len(_PINNED_POOL) >= PINNED_POOL_BLOCKS:
+            victim = max(free, key=lambda e: e[0].numel())                  # too small: make room for a larger one
+            _PINNED_POOL[:] = [e for e in _PINNED_POOL if e is not victim]
+        capacity = -(-nbytes // PINNED_BLOCK_GRAIN) * PINNED_BLOCK_GRAIN
+        try:
+            entry = [torch.empty(capacity, dtype=torch.uint8, pin_memory=True), None]
+        except RuntimeError:
+            return None, None
+        _PINNED_POOL.append(entry)
+    if entry is None:
+        return None, None
+    host = entry[0][:nbytes].view(torch.float64).view(total_rows, nat.CMT_ROW_DOUBLES)
+    rows = host.numpy()
+    entry[1] = weakref.ref(rows)
+    return host, rows
 
 
 _STAGING: Dict[int, list] = {}

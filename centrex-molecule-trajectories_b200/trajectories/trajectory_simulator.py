@@ -31,7 +31,7 @@ from . import _engine as eng
 from . import _hybrid
 from .beamline import Beamline
 from .distributions import CeNTREXPositionDistribution, CeNTREXVelocityDistribution, Distribution
-from .molecule import Molecule
+from .molecule import Molecule, SavedMolecules
 
 __all__ = ["TrajectorySimulator", "Counter", "SimulationResult"]
 
@@ -212,7 +212,7 @@ class TrajectorySimulator:
         save_mask = flat.save_mask(list(apertures_of_interest))
         rank, world = eng.dist_info()
         source = eng.make_source(vdist, xdist)
-        molecules: List[Molecule] = []
+        molecules = SavedMolecules()
 
         if source is not None:
             seed = self._pick_seed(seed, prop.tdev)
@@ -249,7 +249,7 @@ class TrajectorySimulator:
                 # the sized queues were too small after all: once more, with queues that hold everything
                 prop.reset()
                 prop.entry_fraction = None
-                molecules = []
+                molecules = SavedMolecules()
                 chunk = prop.fit_chunk(self.chunk)
                 for k, first in enumerate(range(lo0, hi, chunk)):
                     n = min(chunk, hi - first)
@@ -450,7 +450,7 @@ class TrajectorySimulator:
             per_point, k = [], 0
             for flat in flats:
                 prop.rebind(flat)
-                molecules: List[Molecule] = []
+                molecules = SavedMolecules()
                 for first in range(lo, hi, chunk):
                     n = min(chunk, hi - first)
                     if not save_mask:
@@ -585,22 +585,14 @@ class TrajectorySimulator:
 
     # -- helpers ----------------------------------------------------------------
     @staticmethod
-    def _collect(prop: "eng.Propagator", ic, select=None) -> List[Molecule]:
+    def _collect(prop: "eng.Propagator", ic, select=None) -> SavedMolecules:
         rows, offsets, fate, rows_arrived = prop.trajectories(ic, select=select, defer_sync=True)
-        names = prop.flat.fate_names
-        from_rows = Molecule.from_rows
         lo = np.asarray(offsets).tolist()
-        # each trajectory is a view of its slice of the result block; the shells are built while the rows are
-        # still on their way from the device (nothing below reads a row before rows_arrived())
-        mols = [from_rows(rows[lo[k]:lo[k + 1]], names[f], names[f] == "Detected")
-                for k, f in enumerate(np.asarray(fate).tolist())]
         rows_arrived()
         # (a non-finite value poisons every later row of its trajectory, so the last rows tell)
         last = rows[np.asarray(lo[1:], dtype=np.int64) - 1] if len(lo) > 1 else rows[:0]
-        if last.size and not np.isfinite(last).all():
-            # Beamline.propagate_through ends with trajectory.drop_nans() (beamline.py:38, molecule.py:160-167), which
-            # also strips rows that a non-finite initial condition or an overflow filled with NaN / inf
-            for m in mols:
-                m.trajectory.drop_nans()
-                m.trajectory.n = m.trajectory.t.shape[0]
+        strip = bool(last.size) and not np.isfinite(last).all()
+        # each trajectory is a view of its slice of the result block, wrapped in a Molecule when it is first asked for
+        mols = SavedMolecules()
+        mols.add_rows(rows, lo, np.asarray(fate).tolist(), prop.flat.fate_names, strip)
         return mols

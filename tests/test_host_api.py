@@ -339,3 +339,47 @@ def test_shard_range_partitions_the_index_space():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_saved_molecules_behave_like_the_reference_list():
+    """run_simulation returns its saved molecules as a sequence that makes the Molecule objects on first access
+    (trajectories/molecule.py: SavedMolecules); everything a list of Molecule objects is used for must work."""
+    import copy
+    import pickle
+
+    from trajectories.molecule import Molecule, SavedMolecules
+
+    rng = np.random.default_rng(3)
+    rows = rng.normal(size=(12, 10))
+    names = ["A", "Detected", "B"]
+    s = SavedMolecules()
+    assert len(s) == 0 and s == [] and list(s) == [] and not s
+    s.add_rows(rows, [0, 2, 7, 12], [1, 0, 1], names)
+    extra = Molecule.from_rows(rng.normal(size=(3, 10)), "B", False)
+    s.append(extra)
+    t = SavedMolecules()
+    t.add_rows(rows[:5] + 1.0, [0, 5], [2], names)
+    s.extend(t)
+    assert len(s) == 5 and bool(s)
+    assert [m.aperture_hit for m in s] == ["Detected", "A", "Detected", "B", "B"]
+    assert [m.alive for m in s] == [True, False, True, False, False]
+    assert s[1].trajectory.n == 5 and s[-1].trajectory.n == 5 and s[3] is extra
+    np.testing.assert_array_equal(s[1].trajectory.x, rows[2:7, 0:3])
+    np.testing.assert_array_equal(s[1].trajectory.t, rows[2:7, 9])
+    np.testing.assert_array_equal(s[4].trajectory.v, rows[:5, 3:6] + 1.0)
+    assert s[0] is s[0] and s[::2][1] is s[2] and isinstance(s[1:3], list) and len(s[1:3]) == 2
+    s[2].alive = False                              # a molecule, once made, is the object the caller keeps seeing
+    assert [m.alive for m in s][2] is False
+    with pytest.raises(IndexError):
+        s[5]
+    assert s == list(s) and s != [] and (s + [extra])[5] is extra and len(s) == 5
+    for clone in (pickle.loads(pickle.dumps(s)), copy.deepcopy(s)):
+        assert len(clone) == 5 and [m.aperture_hit for m in clone] == [m.aperture_hit for m in s]
+        np.testing.assert_array_equal(clone[1].trajectory.a, s[1].trajectory.a)
+
+    # rows poisoned by a non-finite value are stripped when the molecule is made, as Beamline.propagate_through does
+    bad = rows.copy()
+    bad[5:7] = np.nan
+    u = SavedMolecules()
+    u.add_rows(bad, [0, 2, 7, 12], [1, 0, 1], names, strip_nans=True)
+    assert u[1].trajectory.n == 3 and u[1].trajectory.x.shape == (3, 3) and u[0].trajectory.n == 2
