@@ -8,6 +8,7 @@ include/cmt.h.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -638,6 +639,7 @@ class Propagator:
 PINNED_POOL_BLOCKS = 3
 PINNED_BLOCK_GRAIN = 32 << 20
 _PINNED_POOL: list = []       # [block (uint8 tensor, page-locked), weakref to the array last handed out over it or None]
+_PINNED_LOCK = threading.Lock()
 
 
 def _pinned_rows(total_rows: int):
@@ -646,6 +648,11 @@ def _pinned_rows(total_rows: int):
 
     torch = _torch()
     nbytes = total_rows * nat.CMT_ROW_DOUBLES * 8
+    with _PINNED_LOCK:          # two threads running simulations must not be handed the same free block
+        return _pinned_rows_locked(torch, weakref, total_rows, nbytes)
+
+
+def _pinned_rows_locked(torch, weakref, total_rows: int, nbytes: int):
     free = [e for e in _PINNED_POOL if e[1] is None or e[1]() is None]
     fit = [e for e in free if e[0].numel() >= nbytes]
     entry = min(fit, key=lambda e: e[0].numel()) if fit else None
