@@ -832,7 +832,31 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
         int seg = std::max(1, tune_seg);
         if (n_steps >= (1 << (63 - SEG_INDEX_BITS))) seg = n_steps;                 // the step count would not fit its bit field
         else if ((n_steps + seg - 1) / seg > max_seg) seg = (n_steps + max_seg - 1) / max_seg;
-        const int n_seg = std::max(1, (n_steps + seg - 1) / seg);
+        int n_seg = std::max(1, (n_steps + seg - 1) / seg);
+        // experiments only: CMT_TUNE_SEG_PLAN="75,75,150,300" gives every launch its own number of steps (the last entry
+        // repeats until the lens is through)
+        static const std::vector<int> tune_plan = [] {
+            std::vector<int> v;
+            if (const char *e = getenv("CMT_TUNE_SEG_PLAN")) {
+                for (const char *p = e; *p;) {
+                    char *end = nullptr;
+                    const long k = strtol(p, &end, 10);
+                    if (end == p) break;
+                    if (k > 0) v.push_back((int)k);
+                    p = *end ? end + 1 : end;
+                }
+            }
+            return v;
+        }();
+        std::vector<int> plan;
+        if (!tune_plan.empty() && n_steps < (1 << (63 - SEG_INDEX_BITS))) {
+            for (int done = 0, k = 0; done < n_steps; ++k) {
+                const int len = tune_plan[std::min<size_t>(k, tune_plan.size() - 1)];
+                plan.push_back(len);
+                done += len;
+            }
+            if ((int)plan.size() <= max_seg) n_seg = (int)plan.size(); else plan.clear();
+        }
         const int64_t max_ctas = (n + LENS_THREADS - 1) / LENS_THREADS;
         cfg.gridDim = dim3((unsigned)std::min<int64_t>(max_ctas, (int64_t)bl->n_sm * seg_per_sm));
         X.q = Q.q + (size_t)(n_seg & 1) * QUEUE_COMPONENTS * (size_t)Q.cap;   // the last segment's unused output array
@@ -852,7 +876,8 @@ static int propagate(const cmt_beamline_t *bl, bool philox, const cmt_source_t *
             B.cursor = B.count + 1;
             {
                 ScopedTimer tk(8 + k, st, 2);
-                CUDA_TRY(cudaLaunchKernelEx(&cfg, seg_fn[contract][copies_log2], bl->P, first_index, *out, A, B, X, seg));
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, seg_fn[contract][copies_log2], bl->P, first_index, *out, A, B, X,
+                                            plan.empty() ? seg : plan[k]));
             }
             count_launch();
         }
