@@ -31,6 +31,33 @@ def _device_run(elements, molecule) -> None:
         molecule.set_aperture_hit(name)
 
 
+def lens_interior(lens, molecule) -> None:
+    """ElectrostaticLens.propagate_inside_lens: the device run of the lens alone from the molecule's last row, minus the
+    row at the entrance plane and the exit row that ElectrostaticLens.propagate_through puts around the integration."""
+    torch = eng._torch()
+    if not getattr(molecule, "alive", True):
+        return
+    prop = eng.Propagator(eng.flatten([lens]))
+    tr = molecule.trajectory
+    last = tr.n - 1
+    state = np.empty((10, 1), dtype=np.float64)
+    state[0:3, 0], state[3:6, 0], state[6:9, 0], state[9, 0] = tr.x[last], tr.v[last], tr.a[last], tr.t[last]
+    if state[8, 0] != 0.0:
+        raise ValueError("a_z != 0 is not supported on the GPU path")
+    rows, offsets, fate = prop.trajectories(torch.from_numpy(state).to(prop.tdev))
+    rows = rows[1:int(offsets[1])]                   # row 0 repeats the molecule's current row
+    name = prop.flat.fate_names[int(fate[0])]
+    if name == "Lens entrance":
+        tr.extend_rows(rows)
+    elif name == "Inside lens":
+        tr.extend_rows(rows[1:])                     # without the row at z0
+    else:
+        tr.extend_rows(rows[1:-1])                   # without the row at z0 and the exit row at z1
+    if name in ("Lens entrance", "Inside lens"):
+        molecule.set_dead()
+        molecule.set_aperture_hit(name)
+
+
 def propagate_molecule(elements, molecule, mark_detected: bool) -> None:
     from ._hybrid import runs_on_device
 

@@ -98,6 +98,18 @@ class ElectrostaticLens(BeamlineElement):
             raise ValueError("only linear a_interp tables are supported on the GPU path")
         return x, y
 
+    def propagate_inside_lens(self, molecule) -> None:
+        """The RK integration between the lens' entrance and exit planes for one molecule standing on the entrance
+        plane (electrostatic_lens.py:79-118): appends one row per step (a = l1 of the step) and marks the molecule
+        "Inside lens" when a step ends beyond the bore.  The reference calls it from `propagate_through` between the
+        row at z0 and the row at z1; here it is that same device run (the trajectory kernel on the lens alone, resumed
+        from the molecule's last row) with those two rows left out.  A molecule that is not on the entrance plane is
+        flown there first, and one that stands outside the bore there is stopped as "Lens entrance", as
+        `propagate_through` would (the reference's method tests neither)."""
+        from .._single import lens_interior
+
+        lens_interior(self, molecule)
+
     def lens_acceleration(self, x):
         """Inspection helper: a(x) [m/s^2] at one position from the table
         (electrostatic_lens.py:215-228).  The simulation itself evaluates the

@@ -75,6 +75,17 @@ class Honeycomb(BeamlineElement):
     def N_steps(self) -> int:
         return 2
 
+    def make_patches(self):
+        """One matplotlib RegularPolygon per cell, as the reference keeps in `patches` (meshes.py:69-82; needs
+        matplotlib).  The GPU path does not use them: its hit test restates `contains_point` (module docstring)."""
+        from matplotlib.patches import RegularPolygon
+
+        return [RegularPolygon((x, y), 6, radius=self.polygon_radius) for x, y in zip(self.xcoords, self.ycoords)]
+
+    @property
+    def patches(self):
+        return self.make_patches()
+
     def plot_mesh(self, ax=None):
         """Draw the cells (needs matplotlib)."""
         import matplotlib.pyplot as plt

@@ -333,6 +333,48 @@ def test_plugin_single_molecule(torch_cuda, golden_dir):
         np.testing.assert_array_equal(got2, got)
 
 
+def test_propagate_inside_lens(torch_cuda, golden_dir):
+    """ElectrostaticLens.propagate_inside_lens (electrostatic_lens.py:79-118) used the way the reference's
+    propagate_through uses it: row at z0 and entrance test by hand, the integration by the method, exit row by hand."""
+    from trajectories.molecule import Molecule
+
+    g = np.load(golden_dir / "lens_biased.npz")
+    bl = lens_beamline((g["table_r"], g["table_a"]))
+    lens = bl.find_element("ES lens")
+    names = list(g["lens_fate_names"])
+    off = g["lens_row_off"]
+    through = 0
+    for k in range(len(g["lens_row_idx"])):
+        i = g["lens_row_idx"][k]
+        want = g["lens_rows"][off[k]:off[k + 1]]
+        m = Molecule()
+        m.init_trajectory(bl, g["ic"][0:3, i], g["ic"][3:6, i])
+        for e in bl.elements:
+            if e is not lens:
+                e.propagate_through(m)
+            else:
+                m.update_trajectory((lens.z0 - m.x()[2]) / m.v()[2])
+                if np.sqrt(np.sum(m.x()[:2] ** 2)) > lens.d / 2:
+                    m.set_dead()
+                    m.set_aperture_hit("Lens entrance")
+                else:
+                    before = m.trajectory.n
+                    lens.propagate_inside_lens(m)
+                    through += 1
+                    if m.alive:
+                        assert m.trajectory.n - before == int(np.rint(lens.L / lens.dz))
+                        m.update_trajectory((lens.z1 - m.x()[2]) / m.v()[2])
+            if not m.alive:
+                break
+        if m.alive:
+            m.set_aperture_hit("Detected")
+        m.trajectory.drop_nans()
+        assert m.aperture_hit == names[g["lens_fate"][i]] and m.alive == bool(g["lens_alive"][i])
+        got = np.concatenate([m.trajectory.x, m.trajectory.v, m.trajectory.a, m.trajectory.t[:, None]], axis=1)
+        assert got.shape == want.shape and relerr(got, want) < TIGHT
+    assert through >= 2
+
+
 def test_arithmetic_selftest(torch_cuda, cuda_lib):
     """The shared-reciprocal division and inline sqrt equal __ddiv_rn / __dsqrt_rn bit for bit."""
     import ctypes as C
