@@ -9,7 +9,7 @@ expect.  Trajectories that come back from the GPU are zero-copy views of one
 from __future__ import annotations
 
 from bisect import bisect_right
-from collections.abc import Sequence
+from collections.abc import MutableSequence
 from dataclasses import dataclass
 
 import numpy as np
@@ -170,7 +170,7 @@ class Molecule:
         attrs["alive"] = self.alive
 
 
-class SavedMolecules(Sequence):
+class SavedMolecules(MutableSequence):
     """The saved molecules of a run, in the order the reference returns them (trajectory_simulator.py:86-91), as a
     list-like sequence whose `Molecule` objects are made the first time they are asked for.
 
@@ -178,7 +178,8 @@ class SavedMolecules(Sequence):
     in a `Molecule` / `Trajectory` pair costs 1.6 us each -- 0.55 s of the 1.2 s that configs[3] takes for its 325 000
     detected molecules, and a burst of garbage for the interpreter's collector -- whether or not the caller ever looks
     at them.  Indexing, slicing (a plain list), iteration, `len`, `==` with lists, `append` / `extend` behave like the
-    list the reference returns; a molecule, once made, stays the same object."""
+    list the reference returns; a molecule, once made, stays the same object.  Operations that rearrange the sequence
+    (item assignment, deletion, `insert`, `pop`, `sort`, `reverse`, ...) first turn it into one plain list."""
 
     def __init__(self, molecules=()):
         self._chunks = []       # (rows, offsets, fates, names, strip) of one launch, or a plain list of Molecule objects
@@ -242,6 +243,40 @@ class SavedMolecules(Sequence):
     def __iter__(self):
         for i in range(len(self)):
             yield self[i]
+
+    # -- rearranging: everything is made, then it is a list ---------------------------------------
+    def _as_list(self) -> list:
+        if not (len(self._chunks) == 1 and isinstance(self._chunks[0], list)):
+            made = [self[i] for i in range(len(self))]
+            self._chunks = [made] if made else []
+            self._starts = [0, len(made)] if made else [0]
+        self._made = {}
+        return self._chunks[0] if self._chunks else []
+
+    def _relist(self, made: list) -> None:
+        self._chunks = [made] if made else []
+        self._starts = [0, len(made)] if made else [0]
+        self._made = {}
+
+    def __setitem__(self, i, value) -> None:
+        made = self._as_list()
+        made[i] = value
+        self._relist(made)
+
+    def __delitem__(self, i) -> None:
+        made = self._as_list()
+        del made[i]
+        self._relist(made)
+
+    def insert(self, i, value) -> None:
+        made = self._as_list()
+        made.insert(i, value)
+        self._relist(made)
+
+    def sort(self, *, key=None, reverse=False) -> None:
+        made = self._as_list()
+        made.sort(key=key, reverse=reverse)
+        self._relist(made)
 
     def __eq__(self, other):
         if isinstance(other, (list, tuple, SavedMolecules)):

@@ -377,6 +377,22 @@ def test_saved_molecules_behave_like_the_reference_list():
         assert len(clone) == 5 and [m.aperture_hit for m in clone] == [m.aperture_hit for m in s]
         np.testing.assert_array_equal(clone[1].trajectory.a, s[1].trajectory.a)
 
+    # list operations that rearrange: the sequence becomes one plain list first
+    v = SavedMolecules()
+    v.add_rows(rows, [0, 2, 7, 12], [1, 0, 1], names)
+    first, second, third = v[0], v[1], v[2]
+    assert v.pop() is third and len(v) == 2
+    v.insert(0, extra)
+    assert v[0] is extra and v[1] is first and v[2] is second and len(v) == 3
+    v.sort(key=lambda m: m.trajectory.n)
+    assert [m.trajectory.n for m in v] == [2, 3, 5]
+    v.reverse()
+    del v[0]
+    v[0] = third
+    assert len(v) == 2 and v[0] is third and v[1] is first and v.index(first) == [third, first].index(first)
+    v.clear()
+    assert len(v) == 0 and v == []
+
     # rows poisoned by a non-finite value are stripped when the molecule is made, as Beamline.propagate_through does
     bad = rows.copy()
     bad[5:7] = np.nan
