@@ -2,6 +2,7 @@
 """Parity of the CUDA path with the CPU oracle at sizes beyond the test suite.
 
     python profiles/parity_at_scale.py > profiles/r02_parity_at_scale.json
+    python profiles/parity_at_scale.py --repeat 10 > profiles/r02_parity_at_scale_x10.json    # 10 seeds per case, one line each
 """
 import json
 import sys
@@ -48,7 +49,7 @@ def compare(label, bl, vdist, xdist, n, seed, math="exact"):
                 filter_fates_equal_unfiltered=bool((fate2 == fate).all()),
                 filter_counters_equal=bool((res2.counters.cpu().numpy() == want["counters"]).all()),
                 filter_rows_steps_equal=bool((res2.work[:2].cpu().numpy() == want["work"][:2]).all()))
-    out = dict(case=label, math=math, molecules=n, **filt, lens_entries=int(want["work"][1] > 0) and int(res.work[3]),
+    out = dict(case=label, math=math, seed=seed, molecules=n, **filt, lens_entries=int(want["work"][1] > 0) and int(res.work[3]),
                rk_steps=int(want["work"][1]), fate_mismatches=int((~same).sum()), max_rel_err=float(rel.max()),
                bit_identical_fraction=float(bit), counters_equal=bool((res.counters.cpu().numpy() == want["counters"]).all()),
                oracle_seconds=round(t_cpu, 2), oracle_threads=threads)
@@ -56,16 +57,20 @@ def compare(label, bl, vdist, xdist, n, seed, math="exact"):
 
 
 def main():
+    repeat = int(sys.argv[sys.argv.index("--repeat") + 1]) if "--repeat" in sys.argv else 1
     v, x = CeNTREXVelocityDistribution(), CeNTREXPositionDistribution()
     lens = lens_beamline(lens_table())
-    compare("lens beamline, standard source", lens, v, x, 50_000_000, 11)
-    compare("lens beamline, collimated source (most molecules enter the lens)", lens,
-            CeNTREXVelocityDistribution(sigmax=3, sigmay=3), x, 4_000_000, 12)
-    compare("apertures-only beamline, standard source", apertures_beamline(), v, x, 50_000_000, 13)
-    compare("SPA beamline, Gaussian position source", spa_beamline(), v, GaussianPositionDistribution(), 50_000_000, 14)
-    compare("lens beamline, standard source", lens, v, x, 50_000_000, 11, math="contracted")
-    compare("lens beamline, collimated source (most molecules enter the lens)", lens,
-            CeNTREXVelocityDistribution(sigmax=3, sigmay=3), x, 4_000_000, 12, math="contracted")
+    for k in range(repeat):
+        s = 100 * k             # seeds 11..14 for the first pass, 111..114 for the second, ...
+        compare("lens beamline, standard source", lens, v, x, 50_000_000, 11 + s)
+        compare("lens beamline, collimated source (most molecules enter the lens)", lens,
+                CeNTREXVelocityDistribution(sigmax=3, sigmay=3), x, 4_000_000, 12 + s)
+        compare("apertures-only beamline, standard source", apertures_beamline(), v, x, 50_000_000, 13 + s)
+        compare("SPA beamline, Gaussian position source", spa_beamline(), v, GaussianPositionDistribution(), 50_000_000, 14 + s)
+        if k == 0:
+            compare("lens beamline, standard source", lens, v, x, 50_000_000, 11, math="contracted")
+            compare("lens beamline, collimated source (most molecules enter the lens)", lens,
+                    CeNTREXVelocityDistribution(sigmax=3, sigmay=3), x, 4_000_000, 12, math="contracted")
 
 
 if __name__ == "__main__":
