@@ -1,0 +1,157 @@
+#!/usr/bin/env python
+"""Randomised beamlines against the CPU oracle: random element types, sizes, positions (overlaps included), lens tables
+and steps, and a source scaled to the geometry, through every launch mode of the library.
+
+    python profiles/fuzz_geometry.py [--cases 200] [--molecules 20000] [--seed 1] > profiles/r02_fuzz_geometry.json
+
+For every case: fates, Counter, work counters and final rows of propagate_ic with final rows (binary64 walk) against
+oracle.propagate; the same molecules asking for fates only (FP32 filter on, both forms) against the same fates.  One JSON
+line per failing case (there should be none) and a summary line."""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (str(ROOT), str(ROOT / "centrex-molecule-trajectories_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+
+def random_beamline(rng):
+    from trajectories.beamline import Beamline
+    from trajectories.beamline_elements.apertures import CircularAperture, FieldPlates, RectangularAperture
+    from trajectories.beamline_elements.electrostatic_lens import ElectrostaticLens, make_interpolator
+
+    scale = float(10 ** rng.uniform(-3, -1))                 # transverse scale of the apertures, 1 mm ... 10 cm
+    n_el = int(rng.integers(1, 8))
+    z = float(rng.uniform(0.01, 0.3))
+    elems, lenses = [], 0
+    for k in range(n_el):
+        L = float(10 ** rng.uniform(-3, -0.3))
+        kind = rng.choice(["circ", "rect", "plates", "lens"], p=[0.4, 0.25, 0.15, 0.2])
+        if kind == "lens" and lenses == 2:
+            kind = "circ"
+        size = scale * float(rng.uniform(0.3, 3.0))
+        x0, y0 = (float(rng.normal(0, 0.2 * scale)), float(rng.normal(0, 0.2 * scale))) if rng.random() < 0.3 else (0.0, 0.0)
+        name = f"{kind}{k}"
+        if kind == "circ":
+            elems.append(CircularAperture(name=name, z0=z, L=L, d=size, x0=x0, y0=y0))
+        elif kind == "rect":
+            elems.append(RectangularAperture(name=name, z0=z, L=L, w=size, h=size * float(rng.uniform(0.3, 2)), x0=x0, y0=y0))
+        elif kind == "plates":
+            elems.append(FieldPlates(name=name, z0=z, L=L, w=size, x0=x0))
+        else:
+            lenses += 1
+            n_pts = int(rng.integers(8, 400))
+            r = np.linspace(0.0, 1.01 * size / 2, n_pts) if rng.random() < 0.8 else \
+                np.concatenate([[0.0], np.sort(rng.uniform(0, 1.01 * size / 2, n_pts - 2)), [1.01 * size / 2]])
+            if np.any(np.diff(r) <= 0):
+                r = np.linspace(0.0, 1.01 * size / 2, n_pts)
+            a = -float(10 ** rng.uniform(3, 6)) * r ** float(rng.uniform(0.8, 2.0)) * float(rng.choice([1.0, 1.0, -1.0]))
+            dz = L / int(rng.integers(1, 700))
+            elems.append(ElectrostaticLens(name=name, z0=z, L=L, d=size, dz=dz, a_interp=make_interpolator(r, a)))
+        z += L * float(rng.uniform(-0.3, 1.5)) if rng.random() < 0.25 else L + float(10 ** rng.uniform(-3, -0.5))
+        z = max(z, 1e-3)
+    return Beamline(elems), scale
+
+
+def random_ics(rng, n, scale, bl):
+    vz = rng.normal(184, 16, n)
+    if rng.random() < 0.2:
+        vz = np.abs(vz) + 1.0
+    z_end = max(e.z0 + e.L for e in bl.elements)
+    spread = scale / max(z_end, 0.1) * 184 * float(rng.uniform(0.2, 3.0))          # transverse speed that fills the apertures
+    ic = np.empty((6, n))
+    th, rr = rng.uniform(0, 2 * np.pi, n), np.sqrt(rng.uniform(0, 1, n)) * scale * float(rng.uniform(0.05, 1.0))
+    ic[0], ic[1], ic[2] = rr * np.cos(th), rr * np.sin(th), float(rng.uniform(0, 0.009))
+    ic[3], ic[4], ic[5] = rng.normal(0, spread, n), rng.normal(0, spread, n), vz
+    return ic
+
+
+def run_case(torch, oracle, eng, nat, rng, n):
+    bl, scale = random_beamline(rng)
+    ic = random_ics(rng, n, scale, bl)
+    want = oracle.propagate(bl.elements, ic)
+    prop = eng.Propagator(bl.elements, 0)
+    dev = torch.from_numpy(np.ascontiguousarray(ic)).cuda()
+    problems = []
+    prop.reset()
+    res = prop.propagate_ic(dev, want_fate=True, want_final=True)
+    torch.cuda.synchronize()
+    fate, fin = res.fate.cpu().numpy(), res.final.cpu().numpy()
+    if not np.array_equal(fate, want["fate"]):
+        problems.append(f"binary64 walk: {(fate != want['fate']).sum()} fates differ")
+    if not np.array_equal(res.counters.cpu().numpy(), want["counters"]):
+        problems.append("Counter differs")
+    work = res.work.cpu().numpy()
+    if want["work"][2] == 0 and not np.array_equal(work[:3], want["work"]):
+        problems.append(f"work counters differ: {work[:3].tolist()} vs {want['work'].tolist()}")
+    same = fate == want["fate"]
+    with np.errstate(invalid="ignore"):
+        a, b = fin[:, same], want["fin"][:, same]
+        ok = np.isfinite(b)
+        rel = np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), 1e-9)
+    worst = float(rel.max()) if rel.size else 0.0
+    if worst > 1e-11:
+        problems.append(f"final rows differ by {worst:.3g}")
+    decided = 0
+    flat = eng.flatten(bl.elements)
+    for flags in (0, 4, 8):                 # constant-threshold filter in pairs, per-molecule tolerances, one molecule per thread
+        nat.lib().cmt_debug_flags(flags)
+        p2 = eng.Propagator(flat, 0)
+        p2.dev = eng.DeviceBeamline(flat, 0, "exact")        # the flags are read when a handle is created: bypass the cache
+        p2.reset()
+        r2 = p2.propagate_ic(dev, want_fate=True, want_final=False)
+        torch.cuda.synchronize()
+        f2 = r2.fate.cpu().numpy()
+        if not np.array_equal(f2, want["fate"]):
+            problems.append(f"filter (debug flags {flags}): {(f2 != want['fate']).sum()} fates differ")
+        if not np.array_equal(r2.counters.cpu().numpy(), want["counters"]):
+            problems.append(f"filter (debug flags {flags}): Counter differs")
+        if flags == 0:
+            decided = int(r2.work[5])
+    nat.lib().cmt_debug_flags(0)
+    desc = [(type(e).__name__, round(e.z0, 5), round(e.L, 5)) for e in bl.elements]
+    return problems, dict(elements=desc, scale=scale, fates=np.bincount(want["fate"], minlength=len(want["counters"])).tolist(),
+                          rk_steps=int(want["work"][1]), out_of_range=int(want["work"][2]), filter_decided=decided, worst_rel=worst)
+
+
+def main():
+    import torch
+    from oracle import oracle
+    from trajectories import _engine as eng
+    from trajectories import _native as nat
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=200)
+    ap.add_argument("--molecules", type=int, default=20000)
+    ap.add_argument("--seed", type=int, default=1)
+    args = ap.parse_args()
+    rng = np.random.default_rng(args.seed)
+    bad = total_rk = total_decided = with_lens = oob_cases = 0
+    worst = 0.0
+    distinct, through = [], []
+    for c in range(args.cases):
+        problems, info = run_case(torch, oracle, eng, nat, rng, args.molecules)
+        total_rk += info["rk_steps"]
+        total_decided += info["filter_decided"]
+        with_lens += any(t == "ElectrostaticLens" for t, _, _ in info["elements"])
+        oob_cases += info["out_of_range"] > 0
+        worst = max(worst, info["worst_rel"])
+        distinct.append(sum(1 for f in info["fates"] if f > 0))
+        through.append(info["fates"][-1] / args.molecules if info["fates"] else 0.0)
+        if problems:
+            bad += 1
+            print(json.dumps(dict(case=c, problems=problems, **info)), flush=True)
+    print(json.dumps(dict(cases=args.cases, molecules_per_case=args.molecules, seed=args.seed, failing_cases=bad,
+                          cases_with_a_lens=with_lens, cases_with_out_of_table_evaluations=oob_cases, rk_steps=total_rk,
+                          fates_decided_by_the_filter=total_decided, worst_relative_difference=worst,
+                          mean_distinct_fates_per_case=float(np.mean(distinct)),
+                          share_of_cases_with_three_or_more_fates=float(np.mean(np.array(distinct) >= 3)))))
+
+
+if __name__ == "__main__":
+    main()

@@ -900,3 +900,24 @@ def test_run_size_arithmetic_of_the_reference(torch_cuda):
     assert set(sim.results) == {"small", "odd"} and sim.results["odd"].counter is sim.counter
     sim.run_simulation(bl, "float", N_traj=1e4, n_jobs=1)               # scripts pass floats (argparse type=float)
     assert sum(sim.counter.counter_dict.values()) == 10_000
+
+
+def test_random_beamlines(torch_cuda):
+    """Randomised geometry (profiles/fuzz_geometry.py: element types, sizes, positions with overlaps, lens tables and
+    steps, a source scaled to the apertures): binary64 walk and all three forms of the FP32 filter against the oracle."""
+    import importlib.util
+    from pathlib import Path
+
+    from trajectories import _engine as eng
+    from trajectories import _native as nat
+
+    spec = importlib.util.spec_from_file_location("fuzz_geometry", Path(__file__).resolve().parent.parent / "profiles" / "fuzz_geometry.py")
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    rng = np.random.default_rng(2026)
+    lens_cases = 0
+    for c in range(24):
+        problems, info = fuzz.run_case(torch_cuda, oracle, eng, nat, rng, 8000)
+        assert not problems, (c, problems, info)
+        lens_cases += any(t == "ElectrostaticLens" for t, _, _ in info["elements"])
+    assert lens_cases >= 5
