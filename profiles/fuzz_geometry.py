@@ -5,8 +5,9 @@ and steps, and a source scaled to the geometry, through every launch mode of the
     python profiles/fuzz_geometry.py [--cases 200] [--molecules 20000] [--seed 1] > profiles/r02_fuzz_geometry.json
 
 For every case: fates, Counter, work counters and final rows of propagate_ic with final rows (binary64 walk) against
-oracle.propagate; the same molecules asking for fates only (FP32 filter on, both forms) against the same fates.  One JSON
-line per failing case (there should be none) and a summary line."""
+oracle.propagate; the same molecules asking for fates only (FP32 filter on, all forms) against the same fates; a Philox run
+from a random device source against the oracle's Philox run, with the filter on and off, and in contracted arithmetic.
+One JSON line per failing case (there should be none) and a summary line."""
 import argparse
 import json
 import sys
@@ -114,9 +115,48 @@ def run_case(torch, oracle, eng, nat, rng, n):
         if flags == 0:
             decided = int(r2.work[5])
     nat.lib().cmt_debug_flags(0)
+
+    # The device source on the same geometry: Counter of a Philox run against the oracle's own Philox run (identical
+    # integer stream; the transforms differ by ulps between CUDA's and glibc's libm, so a molecule within ~1e-13 of an
+    # edge may land on the other side), filter on against filter off on the device (must be identical), and the
+    # contracted arithmetic against the exact one.
+    from trajectories.distributions import (CeNTREXPositionDistribution, CeNTREXVelocityDistribution,
+                                            GaussianPositionDistribution)
+
+    z_end = max(e.z0 + e.L for e in bl.elements)
+    spread = scale / max(z_end, 0.1) * 184 * float(rng.uniform(0.2, 3.0))
+    vd = CeNTREXVelocityDistribution(sigmax=spread, sigmay=spread * float(rng.uniform(0.5, 2)), vz=float(rng.uniform(100, 300)),
+                                     sigmaz=float(rng.uniform(1, 25)))
+    zs = float(rng.uniform(0, 0.009))
+    xd = CeNTREXPositionDistribution(d=scale * float(rng.uniform(0.1, 2)), z=zs) if rng.random() < 0.5 else \
+        GaussianPositionDistribution(sigmax=scale * float(rng.uniform(0.05, 1)), sigmay=scale * float(rng.uniform(0.05, 1)), z=zs)
+    seed, first = int(rng.integers(0, 2 ** 62)), int(rng.integers(0, 2 ** 40))
+    ref = oracle.run(bl.elements, oracle.make_source(vd, xd), seed, first, n)
+    src = eng.make_source(vd, xd)
+    runs = {}
+    for label, flags, math in (("filter", 0, "exact"), ("no filter", 2, "exact"), ("contracted", 0, "contracted")):
+        nat.lib().cmt_debug_flags(flags)
+        p3 = eng.Propagator(flat, 0, math=math)
+        p3.dev = eng.DeviceBeamline(flat, 0, math)
+        p3.reset()
+        p3.propagate_philox(src, seed, first, n)
+        torch.cuda.synchronize()
+        runs[label] = (p3.counters.cpu().numpy().copy(), p3.work.cpu().numpy().copy())
+    nat.lib().cmt_debug_flags(0)
+    if not np.array_equal(runs["filter"][0], runs["no filter"][0]) or not np.array_equal(runs["filter"][1][:3], runs["no filter"][1][:3]):
+        problems.append("Philox run: filter on and off differ")
+    moved = int(np.abs(runs["filter"][0] - ref["counters"]).sum()) // 2
+    if moved > 2:
+        problems.append(f"Philox run: {moved} molecules counted differently from the oracle's run")
+    # (a defocusing random table amplifies the 1e-13 differences of the relaxed roundings exponentially along the lens,
+    # so more than the odd molecule can change sides there: 5 of 20 000 in the worst of 500 cases)
+    moved_c = int(np.abs(runs["contracted"][0] - runs["filter"][0]).sum()) // 2
+    if moved_c > max(2, n // 1000):
+        problems.append(f"contracted arithmetic: {moved_c} fates differ from the exact run")
     desc = [(type(e).__name__, round(e.z0, 5), round(e.L, 5)) for e in bl.elements]
     return problems, dict(elements=desc, scale=scale, fates=np.bincount(want["fate"], minlength=len(want["counters"])).tolist(),
-                          rk_steps=int(want["work"][1]), out_of_range=int(want["work"][2]), filter_decided=decided, worst_rel=worst)
+                          rk_steps=int(want["work"][1]), out_of_range=int(want["work"][2]), filter_decided=decided, worst_rel=worst,
+                          philox_moved=moved, contracted_moved=moved_c)
 
 
 def main():
@@ -134,6 +174,7 @@ def main():
     bad = total_rk = total_decided = with_lens = oob_cases = 0
     worst = 0.0
     distinct, through = [], []
+    philox_moved = contracted_moved = 0
     for c in range(args.cases):
         problems, info = run_case(torch, oracle, eng, nat, rng, args.molecules)
         total_rk += info["rk_steps"]
@@ -141,6 +182,8 @@ def main():
         with_lens += any(t == "ElectrostaticLens" for t, _, _ in info["elements"])
         oob_cases += info["out_of_range"] > 0
         worst = max(worst, info["worst_rel"])
+        philox_moved += info["philox_moved"]
+        contracted_moved += info["contracted_moved"]
         distinct.append(sum(1 for f in info["fates"] if f > 0))
         through.append(info["fates"][-1] / args.molecules if info["fates"] else 0.0)
         if problems:
@@ -149,6 +192,8 @@ def main():
     print(json.dumps(dict(cases=args.cases, molecules_per_case=args.molecules, seed=args.seed, failing_cases=bad,
                           cases_with_a_lens=with_lens, cases_with_out_of_table_evaluations=oob_cases, rk_steps=total_rk,
                           fates_decided_by_the_filter=total_decided, worst_relative_difference=worst,
+                          philox_molecules_counted_differently_from_the_oracle_run=philox_moved,
+                          contracted_fates_different_from_exact=contracted_moved,
                           mean_distinct_fates_per_case=float(np.mean(distinct)),
                           share_of_cases_with_three_or_more_fates=float(np.mean(np.array(distinct) >= 3)))))
 
