@@ -25,16 +25,19 @@ def random_beamline(rng):
     from trajectories.beamline import Beamline
     from trajectories.beamline_elements.apertures import CircularAperture, FieldPlates, RectangularAperture
     from trajectories.beamline_elements.electrostatic_lens import ElectrostaticLens, make_interpolator
+    from trajectories.beamline_elements.meshes import Honeycomb
 
     scale = float(10 ** rng.uniform(-3, -1))                 # transverse scale of the apertures, 1 mm ... 10 cm
     n_el = int(rng.integers(1, 8))
     z = float(rng.uniform(0.01, 0.3))
-    elems, lenses = [], 0
+    elems, lenses, meshes = [], 0, 0
     for k in range(n_el):
         L = float(10 ** rng.uniform(-3, -0.3))
-        kind = rng.choice(["circ", "rect", "plates", "lens"], p=[0.4, 0.25, 0.15, 0.2])
+        kind = rng.choice(["circ", "rect", "plates", "lens", "mesh"], p=[0.36, 0.22, 0.14, 0.2, 0.08])
         if kind == "lens" and lenses == 2:
             kind = "circ"
+        if kind == "mesh" and meshes == 1:
+            kind = "rect"
         size = scale * float(rng.uniform(0.3, 3.0))
         x0, y0 = (float(rng.normal(0, 0.2 * scale)), float(rng.normal(0, 0.2 * scale))) if rng.random() < 0.3 else (0.0, 0.0)
         name = f"{kind}{k}"
@@ -44,6 +47,11 @@ def random_beamline(rng):
             elems.append(RectangularAperture(name=name, z0=z, L=L, w=size, h=size * float(rng.uniform(0.3, 2)), x0=x0, y0=y0))
         elif kind == "plates":
             elems.append(FieldPlates(name=name, z0=z, L=L, w=size, x0=x0))
+        elif kind == "mesh":
+            meshes += 1
+            wall = size / float(rng.uniform(3, 24))
+            elems.append(Honeycomb(name=name, z0=z, L=L, width=size, height=size * float(rng.uniform(0.5, 1.5)),
+                                   cell_wall_length=wall, cell_wall_thickness=wall * float(rng.uniform(0.02, 0.3))))
         else:
             lenses += 1
             n_pts = int(rng.integers(8, 400))
@@ -171,7 +179,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
-    bad = total_rk = total_decided = with_lens = oob_cases = 0
+    bad = total_rk = total_decided = with_lens = with_mesh = oob_cases = 0
     worst = 0.0
     distinct, through = [], []
     philox_moved = contracted_moved = 0
@@ -180,6 +188,7 @@ def main():
         total_rk += info["rk_steps"]
         total_decided += info["filter_decided"]
         with_lens += any(t == "ElectrostaticLens" for t, _, _ in info["elements"])
+        with_mesh += any(t == "Honeycomb" for t, _, _ in info["elements"])
         oob_cases += info["out_of_range"] > 0
         worst = max(worst, info["worst_rel"])
         philox_moved += info["philox_moved"]
@@ -190,7 +199,7 @@ def main():
             bad += 1
             print(json.dumps(dict(case=c, problems=problems, **info)), flush=True)
     print(json.dumps(dict(cases=args.cases, molecules_per_case=args.molecules, seed=args.seed, failing_cases=bad,
-                          cases_with_a_lens=with_lens, cases_with_out_of_table_evaluations=oob_cases, rk_steps=total_rk,
+                          cases_with_a_lens=with_lens, cases_with_a_honeycomb=with_mesh, cases_with_out_of_table_evaluations=oob_cases, rk_steps=total_rk,
                           fates_decided_by_the_filter=total_decided, worst_relative_difference=worst,
                           philox_molecules_counted_differently_from_the_oracle_run=philox_moved,
                           contracted_fates_different_from_exact=contracted_moved,
