@@ -77,6 +77,22 @@ def random_ics(rng, n, scale, bl):
     th, rr = rng.uniform(0, 2 * np.pi, n), np.sqrt(rng.uniform(0, 1, n)) * scale * float(rng.uniform(0.05, 1.0))
     ic[0], ic[1], ic[2] = rr * np.cos(th), rr * np.sin(th), float(rng.uniform(0, 0.009))
     ic[3], ic[4], ic[5] = rng.normal(0, spread, n), rng.normal(0, spread, n), vz
+    # hostile molecules among them: vz = 0 or negative, NaN / inf / huge / tiny / subnormal components, -0.0, a start
+    # exactly on the first plane
+    k = np.arange(n) % 97
+    ic[5, k == 1] = 0.0
+    ic[5, k == 2] *= -1
+    ic[0, k == 3] = np.nan
+    ic[4, k == 4] = np.inf
+    ic[5, k == 5] = 1e-300
+    ic[5, k == 6] = 1e300
+    ic[0, k == 7] = 1e200
+    ic[2, k == 8] = min(e.z0 for e in bl.elements)
+    ic[3, k == 9] = -0.0
+    ic[1, k == 10] = 5e-324
+    ic[5, k == 11] = np.nan
+    ic[0, k == 12], ic[1, k == 12] = 0.0, 0.0          # on the axis: r = 0 in a lens
+    ic[3, k == 13], ic[4, k == 13] = 0.0, 0.0
     return ic
 
 
@@ -99,13 +115,32 @@ def run_case(torch, oracle, eng, nat, rng, n):
     if want["work"][2] == 0 and not np.array_equal(work[:3], want["work"]):
         problems.append(f"work counters differ: {work[:3].tolist()} vs {want['work'].tolist()}")
     same = fate == want["fate"]
-    with np.errstate(invalid="ignore"):
+    with np.errstate(invalid="ignore", over="ignore"):
         a, b = fin[:, same], want["fin"][:, same]
         ok = np.isfinite(b)
         rel = np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), 1e-9)
+        odd = ~ok & ~((np.isnan(a) & np.isnan(b)) | (a == b))           # non-finite values must be the same kind
     worst = float(rel.max()) if rel.size else 0.0
     if worst > 1e-11:
         problems.append(f"final rows differ by {worst:.3g}")
+    if odd.any():
+        problems.append(f"{int(odd.sum())} non-finite final-row values differ in kind")
+    # full trajectories of the first molecules through the same beamline
+    m = min(n, 194)
+    rows, offs, _ = prop.trajectories(dev[:, :m].contiguous())
+    w2 = oracle.propagate(bl.elements, ic[:, :m], want_rows=True)
+    if not np.array_equal(np.diff(offs), w2["n_rows"]):
+        problems.append("row counts of the trajectories differ")
+    else:
+        for k in range(m):
+            g_, w_ = rows[offs[k]:offs[k + 1]], w2["rows"][k, : w2["n_rows"][k]]
+            with np.errstate(invalid="ignore", over="ignore"):
+                fin_ok = np.isfinite(w_)
+                r_ = np.abs(g_[fin_ok] - w_[fin_ok]) / np.maximum(np.abs(w_[fin_ok]), 1e-9)
+                bad_kind = ~fin_ok & ~((np.isnan(g_) & np.isnan(w_)) | (g_ == w_))
+            if (r_.size and r_.max() > 1e-11) or bad_kind.any():
+                problems.append(f"trajectory {k} differs ({float(r_.max()) if r_.size else 0:.3g})")
+                break
     decided = 0
     flat = eng.flatten(bl.elements)
     for flags in (0, 4, 8):                 # constant-threshold filter in pairs, per-molecule tolerances, one molecule per thread
