@@ -142,6 +142,38 @@ def run_case(torch, oracle, eng, nat, rng, n):
                 problems.append(f"trajectory {k} differs ({float(r_.max()) if r_.size else 0:.3g})")
                 break
     decided = 0
+    # plane crossings on the device (crossing_kernel) against the package's host mirror of the reference's
+    # post-processing on the oracle's rows: random planes, element planes among them
+    if "rows" in w2:
+        from trajectories.molecule import Molecule
+        from trajectories.post_processing import state_at_plane
+
+        z_lo, z_hi = min(e.z0 for e in bl.elements), max(e.z0 + e.L for e in bl.elements)
+        planes = list(rng.uniform(0.0, 1.2 * z_hi, 5)) + [bl.elements[0].z0, bl.elements[-1].z0 + bl.elements[-1].L, 0.5 * (z_lo + z_hi)]
+        out, valid, _ = prop.plane_crossings(dev[:, :m].contiguous(), planes)
+        out, valid = out.cpu().numpy(), valid.cpu().numpy()
+        for k in range(m):
+            if not np.isfinite(ic[:, k]).all() or not np.isfinite(w2["rows"][k, : w2["n_rows"][k]]).all():
+                continue                    # the host mirror's comparisons on NaN rows are not what is under test here
+            mol = Molecule.from_rows(w2["rows"][k, : w2["n_rows"][k]], "", True)
+            for q, zq in enumerate(planes):
+                with np.errstate(all="ignore"):
+                    st = state_at_plane(mol, float(zq))
+                if (st is not None) != bool(valid[q, k]):
+                    problems.append(f"plane {zq:.6g}: molecule {k} reaches it on one side only")
+                    break
+                if st is not None:
+                    ref_v = np.concatenate([st[0][:2], st[1]])
+                    with np.errstate(all="ignore"):
+                        okv = np.isfinite(ref_v)
+                        err = np.abs(out[q, :, k][okv] - ref_v[okv]) / np.maximum(np.abs(ref_v[okv]), 1e-9)
+                    if err.size and err.max() > 1e-10:
+                        problems.append(f"plane {zq:.6g}: molecule {k} differs by {float(err.max()):.3g}")
+                        break
+            else:
+                continue
+            break
+
     flat = eng.flatten(bl.elements)
     for flags in (0, 4, 8):                 # constant-threshold filter in pairs, per-molecule tolerances, one molecule per thread
         nat.lib().cmt_debug_flags(flags)
